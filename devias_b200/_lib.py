@@ -1,0 +1,67 @@
+"""ctypes binding of the C-ABI shared library (include/devias_b200.h).
+
+The library is built in-tree (devias_b200/csrc/libdevias_b200.so) by `__graft_entry__.build()` or
+`make -C devias_b200/csrc`.  There is deliberately NO fallback: if the library is missing or a call
+fails, a RuntimeError is raised (BASELINE.json north_star: "no CPU fallback").
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, 'csrc')
+LIB_PATH = os.path.join(CSRC, 'libdevias_b200.so')
+
+_lib = None
+
+
+def build(verbose: bool = False) -> str:
+    """Compile every CUDA source for sm_100a (nvcc cross-compiles without a GPU)."""
+    r = subprocess.run(['make', '-C', CSRC, '-j8'], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError('devias_b200: building the CUDA library failed:\n' + r.stdout[-4000:] + r.stderr[-4000:])
+    if verbose:
+        print(r.stdout[-2000:])
+    return LIB_PATH
+
+
+_P = c_void_p
+_SIGS = {
+    'devias_abi_version': (c_int, []),
+    'devias_last_error': (c_char_p, []),
+    'devias_launch_count': (c_int64, []),
+    'devias_gemm_bf16': (c_int, [_P, c_int64, c_int, _P, c_int64, c_int, c_int, c_int, c_int, c_int, _P, c_int64, _P,
+                                 c_int64, _P, _P, c_int64, c_int, _P, c_int, c_int, _P]),
+}
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise RuntimeError(f'devias_b200: {LIB_PATH} is missing -- run __graft_entry__.build() '
+                               f'(or make -C devias_b200/csrc). There is no CPU/PyTorch fallback.')
+        l = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(l, name)  # AttributeError if the .so is stale: fail loudly
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def exported_symbols():
+    return list(_SIGS.keys())
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = lib().devias_last_error()
+        raise RuntimeError(f'devias_b200.{what} failed (status {rc}): {msg.decode() if msg else "?"}')
+
+
+def launch_count() -> int:
+    return int(lib().devias_launch_count())

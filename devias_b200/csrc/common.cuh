@@ -1,0 +1,43 @@
+// Host-side helpers shared by the C-ABI launchers: status codes, TMA tensor-map encoding.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "../../include/devias_b200.h"
+
+namespace dv {
+
+#define DV_CHECK_CUDA(expr)                                                                           \
+  do {                                                                                                \
+    cudaError_t _e = (expr);                                                                          \
+    if (_e != cudaSuccess) {                                                                          \
+      dv::set_last_error(#expr, cudaGetErrorString(_e), __FILE__, __LINE__);                          \
+      return DEVIAS_ERR_CUDA;                                                                         \
+    }                                                                                                 \
+  } while (0)
+
+#define DV_REQUIRE(cond, msg)                                                                         \
+  do {                                                                                                \
+    if (!(cond)) {                                                                                    \
+      dv::set_last_error(#cond, msg, __FILE__, __LINE__);                                             \
+      return DEVIAS_ERR_ARG;                                                                          \
+    }                                                                                                 \
+  } while (0)
+
+void set_last_error(const char* what, const char* detail, const char* file, int line);
+
+// 2-D bf16 row-major tensor map with 128-byte swizzle.  inner = contiguous dim.
+// Returns 0 on success.
+int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                      uint32_t box_inner, uint32_t box_outer);
+// generic N-d (rank<=5) map; dims/strides innermost first, strides in bytes for dims 1..rank-1
+int make_tmap_nd(CUtensorMap* out, CUtensorMapDataType dt, uint32_t rank, const void* base, const uint64_t* dims,
+                 const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz);
+
+int sm_count();
+void count_launch(int n = 1);
+
+}  // namespace dv
