@@ -33,8 +33,17 @@ _SIGS = {
     'devias_abi_version': (c_int, []),
     'devias_last_error': (c_char_p, []),
     'devias_launch_count': (c_int64, []),
+    'devias_profile_begin': (c_int, []),
+    'devias_profile_end': (c_int, [c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
+                                   ctypes.POINTER(c_int64)]),
     'devias_gemm_bf16': (c_int, [_P, c_int64, c_int, _P, c_int64, c_int, c_int, c_int, c_int, c_int, _P, c_int64, _P,
                                  c_int64, _P, _P, c_int64, c_int, _P, c_int, c_int, _P]),
+    'devias_layernorm_fwd': (c_int, [_P, _P, _P, _P, c_int, _P, _P, c_int, c_int, c_float, _P]),
+    'devias_layernorm_bwd': (c_int, [_P, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, _P]),
+    'devias_colsum_bf16': (c_int, [_P, c_int64, c_int, c_int, _P, _P]),
+    'devias_cast_f32_bf16': (c_int, [_P, _P, c_int64, _P]),
+    'devias_scale_rows_cast': (c_int, [_P, _P, c_int, c_int, _P, c_int, _P]),
+    'devias_patchify': (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P]),
 }
 
 
@@ -65,3 +74,14 @@ def check(rc: int, what: str):
 
 def launch_count() -> int:
     return int(lib().devias_launch_count())
+
+
+def profile_begin():
+    check(lib().devias_profile_begin(), 'profile_begin')
+
+
+def profile_end(kind: int):
+    """-> (total device ms, total algorithmic work, launches) of one kernel family since profile_begin()"""
+    ms, work, n = ctypes.c_double(), ctypes.c_double(), c_int64()
+    check(lib().devias_profile_end(kind, ctypes.byref(ms), ctypes.byref(work), ctypes.byref(n)), 'profile_end')
+    return ms.value, work.value, n.value

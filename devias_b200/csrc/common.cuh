@@ -39,5 +39,8 @@ int make_tmap_nd(CUtensorMap* out, CUtensorMapDataType dt, uint32_t rank, const 
 
 int sm_count();
 void count_launch(int n = 1);
+// per-kernel CUDA-event timing, active only between devias_profile_begin/end (kinds: DEVIAS_PROF_*)
+int prof_begin(int kind, double work, cudaStream_t s);
+void prof_end(int id, cudaStream_t s);
 
 }  // namespace dv

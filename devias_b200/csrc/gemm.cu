@@ -276,7 +276,9 @@ static int launch_gemm(const void* a, long long lda, const void* b, long long ld
   const int m_blks = (p.M + kBM - 1) / kBM, n_blks = (p.N + BN - 1) / BN;
   const int tiles = m_blks * n_blks * p.splits;
   const int grid = tiles < sm_count() ? tiles : sm_count();
+  const int prof = prof_begin(DEVIAS_PROF_GEMM, 2.0 * p.M * (double)p.N * p.K, stream);
   kern<<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  prof_end(prof, stream);
   DV_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return DEVIAS_OK;

@@ -3,6 +3,7 @@
 #include <atomic>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "common.cuh"
 
@@ -81,7 +82,56 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64
   return make_tmap_nd(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
+// ---------------------------------------------------------------- optional per-kernel timing (bench.py roofline leg)
+struct ProfRec { cudaEvent_t a, b; int kind; double work; };
+static std::vector<ProfRec> g_prof;
+static size_t g_prof_used = 0;
+static bool g_prof_on = false;
+
+int prof_begin(int kind, double work, cudaStream_t s) {
+  if (!g_prof_on) return -1;
+  if (g_prof_used == g_prof.size()) {
+    ProfRec r{};
+    if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return -1;
+    g_prof.push_back(r);
+  }
+  ProfRec& r = g_prof[g_prof_used];
+  r.kind = kind;
+  r.work = work;
+  cudaEventRecord(r.a, s);
+  return (int)g_prof_used++;
+}
+void prof_end(int id, cudaStream_t s) {
+  if (id >= 0) cudaEventRecord(g_prof[id].b, s);
+}
+
 }  // namespace dv
+
+extern "C" int devias_profile_begin(void) {
+  dv::g_prof_used = 0;
+  dv::g_prof_on = true;
+  return DEVIAS_OK;
+}
+extern "C" int devias_profile_end(int kind, double* total_ms, double* total_work, int64_t* launches) {
+  using namespace dv;
+  g_prof_on = false;
+  DV_CHECK_CUDA(cudaDeviceSynchronize());
+  double ms = 0, work = 0;
+  long long n = 0;
+  for (size_t i = 0; i < g_prof_used; ++i) {
+    if (g_prof[i].kind != kind) continue;
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, g_prof[i].a, g_prof[i].b) == cudaSuccess) {
+      ms += t;
+      work += g_prof[i].work;
+      ++n;
+    }
+  }
+  if (total_ms) *total_ms = ms;
+  if (total_work) *total_work = work;
+  if (launches) *launches = n;
+  return DEVIAS_OK;
+}
 
 extern "C" int devias_abi_version(void) { return 1; }
 extern "C" const char* devias_last_error(void) { return dv::g_err; }

@@ -1,0 +1,102 @@
+"""Data-parallel gradient exchange for the clip batch (the only collective on the DEVIAS path: the DDP / DeepSpeed
+ZeRO-0 all-reduce of run_slot_finetuning.py:552-563).
+
+One process per GPU.  Gradients live in a few flat fp32 buckets (parameters' .grad are views into them, so autograd
+accumulates straight into the communication buffer - no gather/scatter copies); buckets are filled in reverse
+execution order and each one is all-reduced asynchronously (NCCL over NVLink/NVSwitch, its own stream) as soon as its
+last gradient has been accumulated, overlapping the rest of backward.  `finish()` waits and applies the 1/world mean.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+class GradReducer:
+    def __init__(self, module: torch.nn.Module, bucket_mb: float = 48.0, process_group=None, first_bucket_mb: float = 8.0):
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        params = [p for p in module.parameters() if p.requires_grad]
+        params = params[::-1]                                   # ~ reverse execution order: head/agg first, patch_embed last
+        self.params = params
+        self.buckets: List[torch.Tensor] = []
+        self.bucket_of = {}
+        self._views = {}
+        cap = int(first_bucket_mb * (1 << 20) // 4)
+        cur, cur_n = [], 0
+        groups = []
+        for p in params:
+            n = (p.numel() + 7) // 8 * 8
+            if cur and cur_n + n > cap:
+                groups.append(cur)
+                cur, cur_n = [], 0
+                cap = int(bucket_mb * (1 << 20) // 4)
+            cur.append(p)
+            cur_n += n
+        if cur:
+            groups.append(cur)
+        for bi, g in enumerate(groups):
+            total = sum((p.numel() + 7) // 8 * 8 for p in g)
+            flat = torch.zeros(total, device=g[0].device, dtype=torch.float32)
+            off = 0
+            for p in g:
+                self._views[p] = flat[off:off + p.numel()].view(p.shape)
+                self.bucket_of[p] = bi
+                off += (p.numel() + 7) // 8 * 8
+            self.buckets.append(flat)
+        self.sizes = [len(g) for g in groups]
+        self._pending = [0] * len(groups)
+        self._works: List[Optional[object]] = []
+        self._launched = [False] * len(groups)
+        self.enabled = True                                      # set False on gradient-accumulation micro-steps
+        self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in params]
+        self.zero_grad()
+
+    # ------------------------------------------------------------------------------------------
+    def zero_grad(self):
+        """replaces optimizer.zero_grad(): one memset per bucket, .grad views stay attached"""
+        for flat in self.buckets:
+            flat.zero_()
+        for p in self.params:
+            if p.grad is None or p.grad.data_ptr() != self._views[p].data_ptr():
+                p.grad = self._views[p]
+        self._pending = list(self.sizes)
+        self._launched = [False] * len(self.buckets)
+        self._works = []
+
+    def _on_grad(self, p):
+        if not self.enabled:
+            return
+        b = self.bucket_of[p]
+        if p.grad.data_ptr() != self._views[p].data_ptr():       # someone replaced .grad (e.g. set_to_none): re-home it
+            self._views[p].copy_(p.grad)
+            p.grad = self._views[p]
+        self._pending[b] -= 1
+        if self._pending[b] == 0 and not self._launched[b]:
+            self._launch(b)
+
+    def _launch(self, b):
+        self._launched[b] = True
+        if self.world > 1:
+            self._works.append(dist.all_reduce(self.buckets[b], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+
+    def finish(self):
+        """call after backward, before the optimizer step"""
+        if not self.enabled:
+            return
+        for b in range(len(self.buckets)):
+            if not self._launched[b]:                            # parameters that received no gradient this step
+                self._launch(b)
+        for w in self._works:
+            w.wait()
+        self._works = []
+        if self.world > 1:
+            inv = 1.0 / self.world
+            for flat in self.buckets:
+                flat.mul_(inv)
+
+    def remove(self):
+        for h in self._hooks:
+            h.remove()

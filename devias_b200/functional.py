@@ -1,0 +1,187 @@
+"""torch.autograd.Functions that drive the sm_100a kernels for the encoder of the DEVIAS student
+(model/modeling_slot.py:120-152 Block, :155-177 PatchEmbed, :350-377 forward_features).
+
+Every Function launches only kernels from libdevias_b200.so (see include/devias_b200.h).  The
+residual stream is fp32, GEMM operands are bf16 (fp32 accumulation in tensor memory).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import ops
+
+# --------------------------------------------------------------------------------------------
+# side channel: the LayerNorm-backward kernel that produces a residual-stream gradient (fp32) also
+# emits its bf16 copy (the operand of the next dgrad/wgrad GEMMs).  autograd only carries the fp32
+# tensor between Functions; the copy travels here, keyed by (data_ptr, version).
+_bf16_of = {}
+
+
+def _stash_bf16(dx: torch.Tensor, dxb: torch.Tensor):
+    _bf16_of.clear()
+    _bf16_of[(dx.data_ptr(), dx._version)] = dxb
+
+
+def _is_ours(dx: torch.Tensor) -> bool:
+    """True when `dx` was produced (and stashed) by one of our own backward kernels, i.e. nobody else can alias it."""
+    return (dx.data_ptr(), dx._version) in _bf16_of
+
+
+def _take_bf16(dx: torch.Tensor) -> torch.Tensor:
+    t = _bf16_of.pop((dx.data_ptr(), dx._version), None)
+    if t is not None and t.shape == dx.shape:
+        return t
+    return ops.cast_bf16(dx.contiguous())
+
+
+def _flat_zeros(like_list, device):
+    """one zero-filled fp32 buffer carved into views shaped like `like_list` (8-element aligned)."""
+    offs, total = [], 0
+    for t in like_list:
+        offs.append(total)
+        total += (t.numel() + 7) // 8 * 8
+    flat = torch.zeros(total, device=device, dtype=torch.float32)
+    return [flat[o:o + t.numel()].view(t.shape) for o, t in zip(offs, like_list)]
+
+
+def _wgrad_split(rows_out: int, cols_out: int, tokens: int) -> int:
+    """split-K factor so that a weight-gradient GEMM (K = tokens) fills the 148 SMs."""
+    tiles = ((rows_out + 127) // 128) * ((cols_out + 255) // 256)
+    if cols_out % 256 != 0:
+        tiles = ((rows_out + 127) // 128) * ((cols_out + 127) // 128)
+    kblks = (tokens + 63) // 64
+    s = max(1, min(kblks, (2 * 148 + tiles - 1) // tiles))
+    return s
+
+
+# --------------------------------------------------------------------------------------------
+class PatchEmbedFn(torch.autograd.Function):
+    """Conv3d(k=s=(2,16,16)) + flatten/transpose + sin-cos table add (model/modeling_slot.py:171-177, :354-355)
+    as patchify + one tcgen05 GEMM whose epilogue adds bias and the position table."""
+
+    @staticmethod
+    def forward(ctx, clip, weight, bias, w16, pos_table):
+        B = clip.shape[0]
+        patches = ops.patchify(clip)                      # [B*N, 1536] bf16
+        N = patches.shape[0] // B
+        D = weight.shape[0]
+        x0 = ops.gemm(patches, w16.view(D, -1), ops.EPI_RESID_F32, bias=bias, aux=pos_table, aux_row_mod=N)
+        ctx.save_for_backward(patches)
+        ctx.wshape = weight.shape
+        return x0.view(B, N, D)
+
+    @staticmethod
+    def backward(ctx, dx0):
+        (patches,) = ctx.saved_tensors
+        D = ctx.wshape[0]
+        dyb = _take_bf16(dx0).view(-1, D)
+        dw, db = _flat_zeros([torch.empty(D, patches.shape[1], device='meta'), torch.empty(D, device='meta')], dx0.device)
+        ops.gemm(dyb, patches, ops.EPI_ATOMIC_F32, a_mn=True, b_mn=True, out=dw,
+                 split_k=_wgrad_split(D, patches.shape[1], patches.shape[0]))
+        ops.colsum_bf16(dyb, db)
+        return None, dw.view(ctx.wshape), db, None, None
+
+
+# --------------------------------------------------------------------------------------------
+class LayerNormFn(torch.autograd.Function):
+    """nn.LayerNorm over 768 channels on an fp32 input (final encoder norm, model/modeling_slot.py:373)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps, out_dtype):
+        x = x.contiguous()
+        y, mean, rstd = ops.layernorm_fwd(x, weight, bias, eps, out_dtype)
+        ctx.save_for_backward(x, mean, rstd, weight)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, mean, rstd, weight = ctx.saved_tensors
+        dg, db = _flat_zeros([weight, weight], x.device)
+        dx, dxb = ops.layernorm_bwd(dy.contiguous(), x, mean, rstd, weight, dgamma=dg, dbeta=db)
+        _stash_bf16(dx, dxb)
+        return dx, dg, db, None, None
+
+
+# --------------------------------------------------------------------------------------------
+def _attention_fwd(qkv, B, N, H, need_grad):
+    """Softmax attention over the packed qkv [B*N, 3*H*hd] bf16 (q scaled by hd^-0.5 BEFORE q.k^T,
+    model/modeling_slot.py:105-112).  Returns (out [B*N, H*hd] bf16, state for backward)."""
+    from . import attention
+    return attention.attention_fwd(qkv, B, N, H, need_grad)
+
+
+def _attention_bwd(state, dout):
+    from . import attention
+    return attention.attention_bwd(state, dout)
+
+
+class EncoderBlockFn(torch.autograd.Function):
+    """One pre-LN transformer block, forward and backward (model/modeling_slot.py:142-152 with return_attn=False;
+    Attention :95-117; Mlp :60-67; DropPath :36-47 as per-sample row scales s1/s2 fused in the residual epilogues)."""
+
+    @staticmethod
+    def forward(ctx, x, n1w, n1b, qkv_w, q_bias, v_bias, proj_w, proj_b, n2w, n2b, fc1_w, fc1_b, fc2_w, fc2_b,
+                w16, s1, s2, num_heads, eps):
+        B, N, D = x.shape
+        M = B * N
+        x = x.contiguous()
+        qkv16, proj16, fc116, fc216 = w16
+        need_grad = any(ctx.needs_input_grad)
+        xn, mean1, rstd1 = ops.layernorm_fwd(x, n1w, n1b, eps)
+        qkv_bias = torch.cat((q_bias, torch.zeros_like(v_bias), v_bias))       # modeling_slot.py:99
+        qkv = ops.gemm(xn.view(M, D), qkv16, ops.EPI_STORE_BF16, bias=qkv_bias)
+        attn_out, attn_state = _attention_fwd(qkv, B, N, num_heads, need_grad)
+        x1 = ops.gemm(attn_out, proj16, ops.EPI_RESID_F32, bias=proj_b, aux=x.view(M, D), row_scale=s1, rows_per_scale=N)
+        x1n, mean2, rstd2 = ops.layernorm_fwd(x1, n2w, n2b, eps)
+        h_pre, h_act = ops.gemm(x1n, fc116, ops.EPI_GELU_BF16, bias=fc1_b)
+        x2 = ops.gemm(h_act, fc216, ops.EPI_RESID_F32, bias=fc2_b, aux=x1, row_scale=s2, rows_per_scale=N)
+        if need_grad:
+            ctx.save_for_backward(x, mean1, rstd1, xn, attn_out, x1, mean2, rstd2, x1n, h_pre, h_act,
+                                  n1w, n2w, qkv16, proj16, fc116, fc216, s1, s2)
+            ctx.attn_state = attn_state
+            ctx.dims = (B, N, D)
+            ctx.shapes = [t.shape for t in (n1w, n1b, qkv_w, q_bias, v_bias, proj_w, proj_b, n2w, n2b, fc1_w, fc1_b, fc2_w, fc2_b)]
+        return x2.view(B, N, D)
+
+    @staticmethod
+    def backward(ctx, dx2):
+        (x, mean1, rstd1, xn, attn_out, x1, mean2, rstd2, x1n, h_pre, h_act,
+         n1w, n2w, qkv16, proj16, fc116, fc216, s1, s2) = ctx.saved_tensors
+        B, N, D = ctx.dims
+        M = B * N
+        dev = dx2.device
+        dx2 = dx2.contiguous()
+        ours = _is_ours(dx2)   # our own LN-backward output may be updated in place along the residual chain
+        metas = [torch.empty(s, device='meta') for s in ctx.shapes]
+        (dn1w, dn1b, dqkv_w, dq_bias, dv_bias, dproj_w, dproj_b, dn2w, dn2b, dfc1_w, dfc1_b, dfc2_w, dfc2_b) = \
+            _flat_zeros(metas, dev)
+        Hd = fc116.shape[0]
+        # ---- MLP branch: x2 = x1 + s2 * (gelu(x1n W1^T + b1) W2^T + b2)
+        dyb = _take_bf16(dx2) if s2 is None else ops.scale_rows_cast(dx2, s2, N)
+        dyb = dyb.view(M, D)
+        dh = ops.gemm(dyb, fc216, ops.EPI_DGELU_BF16, b_mn=True, aux=h_pre)            # [M, Hd]
+        ops.gemm(dyb, h_act, ops.EPI_ATOMIC_F32, a_mn=True, b_mn=True, out=dfc2_w, split_k=_wgrad_split(D, Hd, M))
+        ops.colsum_bf16(dyb, dfc2_b)
+        dx1n = ops.gemm(dh, fc116, ops.EPI_STORE_BF16, b_mn=True)                        # [M, D]
+        ops.gemm(dh, x1n, ops.EPI_ATOMIC_F32, a_mn=True, b_mn=True, out=dfc1_w, split_k=_wgrad_split(Hd, D, M))
+        ops.colsum_bf16(dh, dfc1_b)
+        del dh
+        dx1, dx1b = ops.layernorm_bwd(dx1n, x1, mean2, rstd2, n2w, d_resid=dx2.view(M, D), dgamma=dn2w, dbeta=dn2b,
+                                       inplace=ours)
+        # ---- attention branch: x1 = x + s1 * (attn(xn) Wp^T + bp)
+        dyb = dx1b if s1 is None else ops.scale_rows_cast(dx1, s1, N)
+        dattn = ops.gemm(dyb, proj16, ops.EPI_STORE_BF16, b_mn=True)                     # [M, D]
+        ops.gemm(dyb, attn_out, ops.EPI_ATOMIC_F32, a_mn=True, b_mn=True, out=dproj_w, split_k=_wgrad_split(D, D, M))
+        ops.colsum_bf16(dyb, dproj_b)
+        dqkv = _attention_bwd(ctx.attn_state, dattn)                                     # [M, 3D] bf16
+        ctx.attn_state = None
+        dxn = ops.gemm(dqkv, qkv16, ops.EPI_STORE_BF16, b_mn=True)                       # [M, D]
+        ops.gemm(dqkv, xn.view(M, D), ops.EPI_ATOMIC_F32, a_mn=True, b_mn=True, out=dqkv_w, split_k=_wgrad_split(3 * D, D, M))
+        ops.colsum_bf16(dqkv[:, :D], dq_bias)
+        ops.colsum_bf16(dqkv[:, 2 * D:], dv_bias)
+        dx, dxb = ops.layernorm_bwd(dxn, x.view(M, D), mean1, rstd1, n1w, d_resid=dx1, dgamma=dn1w, dbeta=dn1b, inplace=True)
+        _stash_bf16(dx, dxb)
+        return (dx.view(B, N, D), dn1w, dn1b, dqkv_w, dq_bias, dv_bias, dproj_w, dproj_b, dn2w, dn2b, dfc1_w, dfc1_b,
+                dfc2_w, dfc2_b, None, None, None, None, None)

@@ -57,3 +57,86 @@ def gemm(a: torch.Tensor, b: torch.Tensor, epilogue: int, *, a_mn=False, b_mn=Fa
         _ptr(aux), 0 if aux is None else aux.stride(0), aux_row_mod, _ptr(row_scale), rows_per_scale, split_k, _stream())
     _lib.check(rc, 'gemm_bf16')
     return (out, out2) if epilogue == EPI_GELU_BF16 else out
+
+
+def layernorm_fwd(x: torch.Tensor, gamma, beta, eps: float, out_dtype=torch.bfloat16, want_stats=True):
+    """x fp32 [..., 768] -> (y, mean, rstd) (include/devias_b200.h: devias_layernorm_fwd)."""
+    _need_cuda(x, gamma, beta)
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    D = x.shape[-1]
+    rows = x.numel() // D
+    y = torch.empty(x.shape, device=x.device, dtype=out_dtype)
+    mean = torch.empty(rows, device=x.device, dtype=torch.float32) if want_stats else None
+    rstd = torch.empty(rows, device=x.device, dtype=torch.float32) if want_stats else None
+    assert out_dtype in (torch.bfloat16, torch.float32)
+    rc = _lib.lib().devias_layernorm_fwd(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(),
+                                         int(out_dtype == torch.bfloat16), _ptr(mean), _ptr(rstd), rows, D, float(eps), _stream())
+    _lib.check(rc, 'layernorm_fwd')
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, d_resid=None, want_dx=True, want_bf16=True, dgamma=None, dbeta=None,
+                  dx_colsum=None, inplace=False):
+    """returns (dx fp32 | None, dx bf16 | None); dgamma/dbeta/dx_colsum are accumulated in place when given.
+    inplace=True writes dx over d_resid (only for gradient buffers this package produced itself)."""
+    _need_cuda(dy, x)
+    assert dy.is_contiguous() and x.is_contiguous() and dy.dtype in (torch.bfloat16, torch.float32)
+    D = x.shape[-1]
+    rows = x.numel() // D
+    dx = None
+    if want_dx:
+        dx = d_resid if (inplace and d_resid is not None) else torch.empty_like(x)
+    if d_resid is not None:
+        assert d_resid.dtype == torch.float32 and d_resid.is_contiguous()
+    dxb = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16) if want_bf16 else None
+    rc = _lib.lib().devias_layernorm_bwd(dy.data_ptr(), int(dy.dtype == torch.bfloat16), x.data_ptr(), mean.data_ptr(),
+                                         rstd.data_ptr(), gamma.data_ptr(), _ptr(d_resid), _ptr(dx), _ptr(dxb), _ptr(dgamma),
+                                         _ptr(dbeta), _ptr(dx_colsum), rows, D, _stream())
+    _lib.check(rc, 'layernorm_bwd')
+    return dx, dxb
+
+
+def colsum_bf16(a: torch.Tensor, out: torch.Tensor):
+    """out[c] += sum_r a[r, c]; a bf16 2-D (row stride allowed), out fp32 [cols]."""
+    _need_cuda(a, out)
+    assert a.dtype == torch.bfloat16 and a.dim() == 2 and a.stride(1) == 1 and out.dtype == torch.float32
+    rc = _lib.lib().devias_colsum_bf16(a.data_ptr(), a.stride(0), a.shape[0], a.shape[1], out.data_ptr(), _stream())
+    _lib.check(rc, 'colsum_bf16')
+    return out
+
+
+def cast_bf16(src: torch.Tensor, dst: Optional[torch.Tensor] = None):
+    _need_cuda(src, dst)
+    assert src.dtype == torch.float32 and src.is_contiguous()
+    if dst is None:
+        dst = torch.empty(src.shape, device=src.device, dtype=torch.bfloat16)
+    assert dst.is_contiguous() and dst.numel() == src.numel()
+    rc = _lib.lib().devias_cast_f32_bf16(src.data_ptr(), dst.data_ptr(), src.numel(), _stream())
+    _lib.check(rc, 'cast_f32_bf16')
+    return dst
+
+
+def scale_rows_cast(src: torch.Tensor, row_scale: torch.Tensor, rows_per_scale: int):
+    _need_cuda(src, row_scale)
+    assert src.dtype == torch.float32 and src.is_contiguous()
+    cols = src.shape[-1]
+    rows = src.numel() // cols
+    dst = torch.empty(src.shape, device=src.device, dtype=torch.bfloat16)
+    rc = _lib.lib().devias_scale_rows_cast(src.data_ptr(), dst.data_ptr(), rows, cols, row_scale.data_ptr(), rows_per_scale, _stream())
+    _lib.check(rc, 'scale_rows_cast')
+    return dst
+
+
+_DT = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
+
+
+def patchify(clip: torch.Tensor):
+    """clip [B,C,T,H,W] (f32/bf16/f16) -> bf16 [B*T/2*H/16*W/16, C*512]"""
+    _need_cuda(clip)
+    assert clip.dim() == 5 and clip.dtype in _DT
+    clip = clip.contiguous()
+    B, C, T, H, W = clip.shape
+    out = torch.empty(B * (T // 2) * (H // 16) * (W // 16), C * 512, device=clip.device, dtype=torch.bfloat16)
+    rc = _lib.lib().devias_patchify(clip.data_ptr(), _DT[clip.dtype], out.data_ptr(), B, C, T, H, W, _stream())
+    _lib.check(rc, 'patchify')
+    return out

@@ -29,6 +29,16 @@ const char* devias_last_error(void);
 /* number of kernels this library has launched since load (monotonic; used for bench.py's gpu_launches) */
 int64_t devias_launch_count(void);
 
+/* Optional per-kernel timing for bench.py's roofline leg: between begin/end every launch of the instrumented kernel
+ * families is bracketed by CUDA events on its own stream; end() synchronises and returns the summed device time (ms),
+ * the summed algorithmic work (FLOPs for GEMM/attention kinds, bytes for streaming kinds) and the launch count. */
+#define DEVIAS_PROF_GEMM 0
+#define DEVIAS_PROF_ATTN 1
+#define DEVIAS_PROF_SLOT 2
+#define DEVIAS_PROF_NORM 3
+int devias_profile_begin(void);
+int devias_profile_end(int kind, double* total_ms, double* total_work, int64_t* launches);
+
 /* ---- GEMM on tcgen05/TMEM fed by TMA ------------------------------------------------------------
  * D[m,n] = sum_k A[m,k] * B[n,k]  (bf16 operands, fp32 accumulation in tensor memory) + fused epilogue.
  * Replaces F.linear / nn.Linear / Conv3d-as-GEMM and their autograd dgrad/wgrad:
@@ -55,6 +65,38 @@ int devias_gemm_bf16(const void* a, int64_t lda, int a_mn_major, const void* b, 
                      int k, int epilogue, void* out, int64_t ldo, void* out2, int64_t ldo2, const float* bias,
                      const void* aux, int64_t ldaux, int aux_row_mod, const float* row_scale, int rows_per_scale,
                      int split_k, void* stream);
+
+/* dtype ids for entry points that accept several input element types */
+#define DEVIAS_DTYPE_F32 0
+#define DEVIAS_DTYPE_BF16 1
+#define DEVIAS_DTYPE_F16 2
+
+/* ---- LayerNorm (dim = 768) ---------------------------------------------------------------------
+ * Forward: y = (x - mean) * rstd * gamma + beta, x fp32 [rows, dim]; y bf16 (y_is_bf16) or fp32; mean/rstd fp32 [rows]
+ * (may be NULL).  Replaces nn.LayerNorm at model/modeling_slot.py:126,132 (eps 1e-6), :373 and
+ * agg_block/attention.py:29-30 (eps 1e-5).
+ * Backward: dx = d_resid + dLN(dy) (fp32, optional) and/or its bf16 copy; dgamma/dbeta/dx_colsum (fp32 [dim], optional)
+ * are ACCUMULATED (+=).  d_resid may be NULL; dx may alias d_resid.  dx_colsum = column sums of dx, i.e. the bias
+ * gradient of the linear layer that produced the residual branch (Block.forward, model/modeling_slot.py:150-151). */
+int devias_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y, int y_is_bf16, float* mean,
+                         float* rstd, int rows, int dim, float eps, void* stream);
+int devias_layernorm_bwd(const void* dy, int dy_is_bf16, const float* x, const float* mean, const float* rstd,
+                         const float* gamma, const float* d_resid, float* dx, void* dx_bf16, float* dgamma, float* dbeta,
+                         float* dx_colsum, int rows, int dim, void* stream);
+/* out[c] += sum_r a[r, c]  (bf16 [rows, cols] with row stride lda) -- bias gradients of qkv / fc1 */
+int devias_colsum_bf16(const void* a, int64_t lda, int rows, int cols, float* out, void* stream);
+
+/* ---- operand preparation ------------------------------------------------------------------------
+ * cast: fp32 master weights -> the bf16 copies the tensor-core kernels read (one launch over the flat weight arena).
+ * patchify: clip [B, C, T, H, W] (f32/bf16/f16) -> bf16 [B*(T/2)*(H/16)*(W/16), C*512] tube-patch rows so that
+ * Conv3d(k=s=(2,16,16)) (model/modeling_slot.py:167-176) becomes devias_gemm_bf16 with the RESID_F32 epilogue adding the
+ * bias and the sin-cos table (:354-355).  row = t*196 + h*14 + w, col = c*512 + dt*256 + dy*16 + dx. */
+int devias_cast_f32_bf16(const float* in, void* out, int64_t n, void* stream);
+/* out_bf16[r,:] = bf16(in_f32[r,:] * row_scale[r / rows_per_scale]) -- gradient entering a drop-path branch (modeling_slot.py:36-47) */
+int devias_scale_rows_cast(const float* in, void* out, int rows, int cols, const float* row_scale, int rows_per_scale,
+                           void* stream);
+int devias_patchify(const void* clip, int clip_dtype, void* out, int batch, int chans, int frames, int height, int width,
+                    void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,89 @@
+"""CPU, world_size 2 over gloo: the bucketed gradient reducer averages gradients exactly like a single process on the
+concatenated batch, leaves all ranks with identical parameters after a step, and handles gradient accumulation."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from devias_b200.ddp import GradReducer
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        return s.getsockname()[1]
+
+
+def _model():
+    torch.manual_seed(0)
+    return torch.nn.Sequential(torch.nn.Linear(37, 64), torch.nn.GELU(), torch.nn.LayerNorm(64), torch.nn.Linear(64, 19))
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        m = _model()
+        red = GradReducer(m, bucket_mb=0.004, first_bucket_mb=0.001)   # tiny buckets -> several of them
+        assert len(red.buckets) > 2
+        opt = torch.optim.SGD(m.parameters(), lr=0.1)
+        g = torch.Generator().manual_seed(1)
+        x = torch.randn(8, 37, generator=g); y = torch.randn(8, 19, generator=g)
+        xs, ys = x.chunk(world)[rank], y.chunk(world)[rank]
+        # step 1: plain
+        red.zero_grad()
+        ((m(xs) - ys) ** 2).mean().backward()
+        red.finish()
+        grads1 = [p.grad.clone().numpy() for p in m.parameters()]
+        opt.step()
+        # step 2: two accumulation micro-steps, exchange on the second
+        red.zero_grad()
+        red.enabled = False
+        ((m(xs[:2]) - ys[:2]) ** 2).mean().backward()
+        red.enabled = True
+        for b in range(len(red.buckets)):
+            red._pending[b] = red.sizes[b]
+        ((m(xs[2:]) - ys[2:]) ** 2).mean().backward()
+        red.finish()
+        opt.step()
+        q.put((rank, grads1, [p.detach().clone().numpy() for p in m.parameters()]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_reducer_world2_matches_single_process():
+    world, port = 2, _free_port()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # single-process reference on the whole batch
+    m = _model()
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(8, 37, generator=g); y = torch.randn(8, 19, generator=g)
+    ((m(x) - y) ** 2).mean().backward()
+    for a, b0, b1 in zip(m.parameters(), res[0][1], res[1][1]):
+        assert torch.allclose(a.grad, torch.from_numpy(b0), atol=1e-6) and (b0 == b1).all()
+    for p0, p1 in zip(res[0][2], res[1][2]):
+        assert (p0 == p1).all()
+
+
+def test_reducer_single_process_is_passthrough():
+    m = _model()
+    red = GradReducer(m)
+    x = torch.randn(4, 37)
+    red.zero_grad()
+    m(x).sum().backward()
+    red.finish()
+    m2 = _model()
+    m2(x).sum().backward()
+    for a, b in zip(m.parameters(), m2.parameters()):
+        assert torch.allclose(a.grad, b.grad)
+        assert a.grad.data_ptr() == red._views[a].data_ptr()
