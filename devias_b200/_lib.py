@@ -38,6 +38,9 @@ _SIGS = {
                                    ctypes.POINTER(c_int64)]),
     'devias_gemm_bf16': (c_int, [_P, c_int64, c_int, _P, c_int64, c_int, c_int, c_int, c_int, c_int, _P, c_int64, _P,
                                  c_int64, _P, _P, c_int64, c_int, _P, c_int, c_int, _P]),
+    'devias_flash_attn_fwd': (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_float, _P]),
+    'devias_flash_attn_bwd': (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, _P]),
+    'devias_slot_stream_fwd': (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, _P]),
     'devias_layernorm_fwd': (c_int, [_P, _P, _P, _P, c_int, _P, _P, c_int, c_int, c_float, _P]),
     'devias_layernorm_bwd': (c_int, [_P, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, _P]),
     'devias_colsum_bf16': (c_int, [_P, c_int64, c_int, c_int, _P, _P]),

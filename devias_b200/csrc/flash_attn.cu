@@ -1,0 +1,629 @@
+// Fused softmax attention for the encoder (model/modeling_slot.py:102-112): out = softmax(scale * Q K^T) V per (clip, head),
+// head_dim 64, sequence 1568 (any N), no mask, no dropout -- the 12 x N x N probability matrix never touches HBM.
+//
+// Forward kernel, one CTA per (clip, head, 128-query tile), two CTAs resident per SM:
+//   warp 0      : TMA producer   (Q once; K_j / V_j 64-key tiles through a 3-stage ring; 3-D tensor map over the packed
+//                                 qkv activation [B, N, 3*H*64] so rows past N are zero-filled)
+//   warp 1      : tcgen05 issuer (S_j = Q K_j^T -> TMEM;  O_j = P_j V_j -> TMEM;  S_{j+1} is issued before P_j is awaited)
+//   warps 2..5  : softmax        (thread = query row: TMEM -> registers, online max/sum in the exp2 domain, P_j -> bf16 ->
+//                                 128B-swizzled smem as the A operand of the second MMA, running O in registers)
+// Backward kernels live below (dQ / dK / dV with recomputed probabilities).
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace dv {
+
+constexpr int kHD = 64;        // head dim
+constexpr int kQT = 128;       // queries per CTA
+constexpr int kKT = 64;        // keys per tile
+constexpr int kKVStages = 3;
+constexpr int kFaThreads = 192;
+
+struct FaSmem {
+  static constexpr int Q_BYTES = kQT * kHD * 2;        // 16 KiB
+  static constexpr int K_BYTES = kKT * kHD * 2;        // 8 KiB
+  static constexpr int V_BYTES = kKT * kHD * 2;        // 8 KiB
+  static constexpr int P_BYTES = kQT * kKT * 2;        // 16 KiB
+  static constexpr int OFF_Q = 0;
+  static constexpr int OFF_K = OFF_Q + Q_BYTES;
+  static constexpr int OFF_V = OFF_K + kKVStages * K_BYTES;
+  static constexpr int OFF_P = OFF_V + kKVStages * V_BYTES;
+  static constexpr int OFF_BAR = OFF_P + 2 * P_BYTES;
+  static constexpr int BYTES = OFF_BAR + 256 + 1024;
+};
+
+struct FaParams {
+  int B, N, H;
+  int Npad;                         // row length of lse2 / delta: N rounded up to a multiple of 128
+  float scale_log2;                 // head_dim^-0.5 * log2(e)
+  __nv_bfloat16* out; long long ldo;  // [B*N, H*64]
+  float* lse2;                      // [B, H, N]  log2-domain log-sum-exp of the scaled scores
+};
+
+__global__ void __launch_bounds__(kFaThreads, 2)
+flash_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const FaParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FaSmem::OFF_BAR);
+  uint64_t* q_full = bars;                 // 1
+  uint64_t* kv_full = bars + 1;            // 3
+  uint64_t* kv_empty = bars + 4;           // 3
+  uint64_t* s_full = bars + 7;             // 2
+  uint64_t* s_empty = bars + 9;            // 2
+  uint64_t* p_full = bars + 11;            // 2
+  uint64_t* p_empty = bars + 13;           // 2
+  uint64_t* o_full = bars + 15;            // 2
+  uint64_t* o_empty = bars + 17;           // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
+
+  const int warp = threadIdx.x >> 5;
+  const int q_tiles = (p.N + kQT - 1) / kQT;
+  const int qt = blockIdx.x % q_tiles;
+  const int bh = blockIdx.x / q_tiles;
+  const int h = bh % p.H, b = bh / p.H;
+  const int q0 = qt * kQT;
+  const int T = (p.N + kKT - 1) / kKT;     // key tiles
+  const int D = p.H * kHD;
+
+  if (warp == 0 && elect_one()) {
+    prefetch_tmap(&tmQ);
+    prefetch_tmap(&tmKV);
+  }
+  if (warp == 1) {
+    if (elect_one()) {
+      mbar_init(q_full, 1);
+      for (int i = 0; i < kKVStages; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4);
+        mbar_init(&p_full[i], 4); mbar_init(&p_empty[i], 1);
+        mbar_init(&o_full[i], 1); mbar_init(&o_empty[i], 4);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<256>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tm_s[2] = {tmem, tmem + 64};
+  const uint32_t tm_o[2] = {tmem + 128, tmem + 192};
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(q_full, FaSmem::Q_BYTES);
+      tma_load_3d(smem + FaSmem::OFF_Q, &tmQ, q_full, h * kHD, q0, b);
+      for (int j = 0; j < T; ++j) {
+        const int st = j % kKVStages;
+        mbar_wait(&kv_empty[st], ((j / kKVStages) & 1) ^ 1);
+        mbar_arrive_expect_tx(&kv_full[st], FaSmem::K_BYTES + FaSmem::V_BYTES);
+        tma_load_3d(smem + FaSmem::OFF_K + st * FaSmem::K_BYTES, &tmKV, &kv_full[st], D + h * kHD, j * kKT, b);
+        tma_load_3d(smem + FaSmem::OFF_V + st * FaSmem::V_BYTES, &tmKV, &kv_full[st], 2 * D + h * kHD, j * kKT, b);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(kQT, kKT, false, false);   // S = Q K^T : both K-major
+      constexpr uint32_t idesc_o = umma_idesc_bf16(kQT, kHD, false, true);    // O = P V   : A K-major, B (=V) MN-major
+      const uint32_t sq = smem_u32(smem + FaSmem::OFF_Q);
+      auto issue_s = [&](int j) {
+        const int st = j % kKVStages;
+        mbar_wait(&kv_full[st], (j / kKVStages) & 1);
+        mbar_wait(&s_empty[j & 1], ((j >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint64_t da = umma_desc_sw128(sq, 0, 1024);
+        const uint64_t db = umma_desc_sw128(smem_u32(smem + FaSmem::OFF_K + st * FaSmem::K_BYTES), 0, 1024);
+#pragma unroll
+        for (int k = 0; k < kHD / 16; ++k) umma_ss(tm_s[j & 1], da + 2 * k, db + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(&s_full[j & 1]);
+      };
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      for (int j = 0; j < T; ++j) {
+        if (j + 1 < T) issue_s(j + 1);
+        const int st = j % kKVStages;
+        mbar_wait(&p_full[j & 1], (j >> 1) & 1);
+        mbar_wait(&o_empty[j & 1], ((j >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint64_t da = umma_desc_sw128(smem_u32(smem + FaSmem::OFF_P + (j & 1) * FaSmem::P_BYTES), 0, 1024);
+        const uint64_t db = umma_desc_sw128(smem_u32(smem + FaSmem::OFF_V + st * FaSmem::V_BYTES), kKT * 128, 1024);
+#pragma unroll
+        for (int k = 0; k < kKT / 16; ++k) umma_ss(tm_o[j & 1], da + 2 * k, db + 128 * k, idesc_o, k > 0 ? 1u : 0u);
+        umma_commit(&o_full[j & 1]);
+        umma_commit(&kv_empty[st]);
+        umma_commit(&p_empty[j & 1]);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    const int lane = (int)lane_id();
+    const int r = q * 32 + lane;                     // query row inside the tile == TMEM lane
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    float m = -INFINITY, l = 0.f;
+    float o[kHD];
+#pragma unroll
+    for (int i = 0; i < kHD; ++i) o[i] = 0.f;
+    uint8_t* p_row_base = smem + FaSmem::OFF_P + r * 128;
+    for (int j = 0; j < T; ++j) {
+      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      tc_fence_after();
+      uint32_t s0[32], s1[32];
+      tmem_ld_32x32b_x32(tm_s[j & 1] + lane_sel, s0);
+      tmem_ld_32x32b_x32(tm_s[j & 1] + lane_sel + 32, s1);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[j & 1]);
+      const int valid = p.N - j * kKT;               // keys valid in this tile (>= 64 except the last)
+      float mx = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        float a = __uint_as_float(s0[i]) * p.scale_log2, c = __uint_as_float(s1[i]) * p.scale_log2;
+        if (i >= valid) a = -INFINITY;
+        if (i + 32 >= valid) c = -INFINITY;
+        s0[i] = __float_as_uint(a); s1[i] = __float_as_uint(c);
+        mx = fmaxf(mx, fmaxf(a, c));
+      }
+      const float m_new = fmaxf(m, mx);
+      const float alpha = fast_exp2(m - m_new);
+      m = m_new;
+      // P_j -> smem (K-major, 128B swizzle: 16-byte chunk c of row r lands at chunk c ^ (r & 7))
+      mbar_wait(&p_empty[j & 1], ((j >> 1) & 1) ^ 1);
+      uint8_t* prow = p_row_base + (j & 1) * FaSmem::P_BYTES;
+      float sum = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float e[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { e[i] = fast_exp2(__uint_as_float(s0[8 * c + i]) - m_new); sum += e[i]; }
+        *reinterpret_cast<uint4*>(prow + ((c ^ (r & 7)) << 4)) =
+            make_uint4(pack_bf16(e[0], e[1]), pack_bf16(e[2], e[3]), pack_bf16(e[4], e[5]), pack_bf16(e[6], e[7]));
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float e[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { e[i] = fast_exp2(__uint_as_float(s1[8 * c + i]) - m_new); sum += e[i]; }
+        *reinterpret_cast<uint4*>(prow + (((c + 4) ^ (r & 7)) << 4)) =
+            make_uint4(pack_bf16(e[0], e[1]), pack_bf16(e[2], e[3]), pack_bf16(e[4], e[5]), pack_bf16(e[6], e[7]));
+      }
+      l = l * alpha + sum;
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[j & 1]);
+      // fold the previous tile's P V product into the running output, then rescale to the new maximum
+      if (j > 0) {
+        mbar_wait(&o_full[(j - 1) & 1], ((j - 1) >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int hlf = 0; hlf < 2; ++hlf) {
+          uint32_t t[32];
+          tmem_ld_32x32b_x32(tm_o[(j - 1) & 1] + lane_sel + 32 * hlf, t);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[32 * hlf + i] = (o[32 * hlf + i] + __uint_as_float(t[i])) * alpha;
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&o_empty[(j - 1) & 1]);
+      }
+    }
+    {
+      const int j = T - 1;
+      mbar_wait(&o_full[j & 1], (j >> 1) & 1);
+      tc_fence_after();
+      const float inv = 1.0f / l;
+#pragma unroll
+      for (int hlf = 0; hlf < 2; ++hlf) {
+        uint32_t t[32];
+        tmem_ld_32x32b_x32(tm_o[j & 1] + lane_sel + 32 * hlf, t);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[32 * hlf + i] = (o[32 * hlf + i] + __uint_as_float(t[i])) * inv;
+      }
+    }
+    const int qi = q0 + r;
+    if (qi < p.N) {
+      uint4* dst = reinterpret_cast<uint4*>(p.out + ((long long)b * p.N + qi) * p.ldo + h * kHD);
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        dst[c] = make_uint4(pack_bf16(o[8 * c], o[8 * c + 1]), pack_bf16(o[8 * c + 2], o[8 * c + 3]),
+                            pack_bf16(o[8 * c + 4], o[8 * c + 5]), pack_bf16(o[8 * c + 6], o[8 * c + 7]));
+      if (p.lse2 != nullptr) p.lse2[((long long)b * p.H + h) * p.Npad + qi] = m + log2f(l);
+    } else if (p.lse2 != nullptr && qi < p.Npad) {
+      p.lse2[((long long)b * p.H + h) * p.Npad + qi] = INFINITY;   // padded queries: exp2(s - inf) = 0 in the backward
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<256>(tmem);
+  }
+}
+
+
+// =====================================================================================================================
+// Backward.  One CTA per (clip, head, 128-key tile); loop over 128-query tiles.  dK/dV accumulate in TMEM for the whole
+// loop; each iteration's dQ partial goes TMEM -> red.global.add.f32 into an fp32 [B*N, H*64] buffer (L2 resident).
+//   S^T = K Q_i^T, dP^T = V dO_i^T            (TMEM, thread = key row)
+//   P^T = exp2(c S^T - lse2[q]),  dS^T = P^T * (dP^T - delta[q])      -> bf16 -> smem (K-major over q, 128B swizzle)
+//   dV += P^T dO_i,  dK += dS^T Q_i,  dQ_i = dS K   (the dS^T tile is re-read as an MN-major A operand)
+// The softmax scale is applied to dK in the epilogue and to dQ in the fp32 -> bf16 conversion kernel.
+//   warp 0 : TMA (K,V once; Q_i, dO_i, lse2_i, delta_i through a 2-stage ring)   warp 1 : tcgen05 issuer
+//   warps 2..9 : compute (lane quarter = warp % 4, column half = (warp - 2) / 4)
+constexpr int kBwdThreads = 320;
+struct FbSmem {
+  static constexpr int TILE = 128 * kHD * 2;            // 16 KiB: a [128 x 64] bf16 operand tile
+  static constexpr int OFF_K = 0;
+  static constexpr int OFF_V = OFF_K + TILE;
+  static constexpr int OFF_Q = OFF_V + TILE;            // 2 stages
+  static constexpr int OFF_DO = OFF_Q + 2 * TILE;       // 2 stages
+  static constexpr int OFF_P = OFF_DO + 2 * TILE;       // P^T  [128 keys x 128 queries] = 2 atoms x 16 KiB
+  static constexpr int OFF_DS = OFF_P + 2 * TILE;       // dS^T
+  static constexpr int OFF_STAT = OFF_DS + 2 * TILE;    // 2 stages x (lse2[128], delta[128]) fp32
+  static constexpr int OFF_BAR = OFF_STAT + 2 * 1024;
+  static constexpr int BYTES = OFF_BAR + 256 + 1024;
+};
+
+struct FbParams {
+  int B, N, H, Npad;
+  float scale, scale_log2;
+  const float* lse2; const float* delta;   // [B, H, Npad]
+  float* dq_acc;                            // [B*N, H*64] fp32, zero-initialised
+  __nv_bfloat16* dqkv; long long ld;        // [B*N, 3*H*64]
+};
+
+__global__ void __launch_bounds__(kBwdThreads, 1)
+flash_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO, const FbParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FbSmem::OFF_BAR);
+  uint64_t* kv_full = bars;            // 1
+  uint64_t* qdo_full = bars + 1;       // 2
+  uint64_t* qdo_empty = bars + 3;      // 2
+  uint64_t* sdp_full = bars + 5;       // 1
+  uint64_t* sdp_empty = bars + 6;      // 1 (8 warps)
+  uint64_t* pds_full = bars + 7;       // 1 (8 warps)
+  uint64_t* pds_empty = bars + 8;      // 1
+  uint64_t* dq_full = bars + 9;        // 2
+  uint64_t* dq_empty = bars + 11;      // 2 (8 warps)
+  uint64_t* acc_full = bars + 13;      // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+
+  const int warp = threadIdx.x >> 5;
+  const int k_tiles = (p.N + 127) / 128;
+  const int kt = blockIdx.x % k_tiles;
+  const int bh = blockIdx.x / k_tiles;
+  const int h = bh % p.H, b = bh / p.H;
+  const int k0 = kt * 128;
+  const int T = (p.N + 127) / 128;       // query tiles
+  const int D = p.H * kHD;
+
+  if (warp == 0 && elect_one()) {
+    prefetch_tmap(&tmQKV);
+    prefetch_tmap(&tmDO);
+  }
+  if (warp == 1) {
+    if (elect_one()) {
+      mbar_init(kv_full, 1);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1);
+        mbar_init(&dq_full[i], 1); mbar_init(&dq_empty[i], 8);
+      }
+      mbar_init(sdp_full, 1); mbar_init(sdp_empty, 8);
+      mbar_init(pds_full, 8); mbar_init(pds_empty, 1);
+      mbar_init(acc_full, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<512>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tm_dk = tmem, tm_dv = tmem + 64, tm_s = tmem + 128, tm_dp = tmem + 256;
+  const uint32_t tm_dq[2] = {tmem + 384, tmem + 448};
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(kv_full, 2 * FbSmem::TILE);
+      tma_load_3d(smem + FbSmem::OFF_K, &tmQKV, kv_full, D + h * kHD, k0, b);
+      tma_load_3d(smem + FbSmem::OFF_V, &tmQKV, kv_full, 2 * D + h * kHD, k0, b);
+      const long long stat_row = ((long long)b * p.H + h) * p.Npad;
+      for (int i = 0; i < T; ++i) {
+        const int st = i & 1;
+        mbar_wait(&qdo_empty[st], ((i >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&qdo_full[st], 2 * FbSmem::TILE + 1024);
+        tma_load_3d(smem + FbSmem::OFF_Q + st * FbSmem::TILE, &tmQKV, &qdo_full[st], h * kHD, i * 128, b);
+        tma_load_3d(smem + FbSmem::OFF_DO + st * FbSmem::TILE, &tmDO, &qdo_full[st], h * kHD, i * 128, b);
+        bulk_load_1d(smem + FbSmem::OFF_STAT + st * 1024, p.lse2 + stat_row + i * 128, 512, &qdo_full[st]);
+        bulk_load_1d(smem + FbSmem::OFF_STAT + st * 1024 + 512, p.delta + stat_row + i * 128, 512, &qdo_full[st]);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);   // [keys x queries] = K . Q^T / V . dO^T
+      constexpr uint32_t idesc_kv = umma_idesc_bf16(128, kHD, false, true);   // [keys x hd]: A = P^T/dS^T (K-major), B = dO/Q (MN-major)
+      constexpr uint32_t idesc_q = umma_idesc_bf16(128, kHD, true, true);     // [queries x hd]: A = dS^T read MN-major, B = K (MN-major)
+      const uint32_t sk = smem_u32(smem + FbSmem::OFF_K), sv = smem_u32(smem + FbSmem::OFF_V);
+      const uint32_t sp = smem_u32(smem + FbSmem::OFF_P), sds = smem_u32(smem + FbSmem::OFF_DS);
+      auto issue_sdp = [&](int i) {
+        const int st = i & 1;
+        mbar_wait(&qdo_full[st], (i >> 1) & 1);
+        mbar_wait(sdp_empty, (i & 1) ^ 1);
+        tc_fence_after();
+        const uint64_t dq_ = umma_desc_sw128(smem_u32(smem + FbSmem::OFF_Q + st * FbSmem::TILE), 0, 1024);
+        const uint64_t ddo = umma_desc_sw128(smem_u32(smem + FbSmem::OFF_DO + st * FbSmem::TILE), 0, 1024);
+        const uint64_t dk_ = umma_desc_sw128(sk, 0, 1024), dv_ = umma_desc_sw128(sv, 0, 1024);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_ss(tm_s, dk_ + 2 * k, dq_ + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_ss(tm_dp, dv_ + 2 * k, ddo + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(sdp_full);
+      };
+      mbar_wait(kv_full, 0);
+      issue_sdp(0);
+      for (int i = 0; i < T; ++i) {
+        if (i + 1 < T) issue_sdp(i + 1);
+        const int st = i & 1;
+        mbar_wait(pds_full, i & 1);
+        tc_fence_after();
+        // B operands, MN-major over the 128 query rows of this stage (one 64-wide atom, 16 rows per UMMA_K)
+        const uint64_t bdo = umma_desc_sw128(smem_u32(smem + FbSmem::OFF_DO + st * FbSmem::TILE), 128 * 128, 1024);
+        const uint64_t bq = umma_desc_sw128(smem_u32(smem + FbSmem::OFF_Q + st * FbSmem::TILE), 128 * 128, 1024);
+        const uint64_t ap = umma_desc_sw128(sp, 0, 1024), ads = umma_desc_sw128(sds, 0, 1024);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {   // K = 128 queries: k-steps 0..3 in atom 0, 4..7 in atom 1 (+16 KiB)
+          const uint64_t aoff = (uint64_t)((k >> 2) * (FbSmem::TILE >> 4) + (k & 3) * 2);
+          umma_ss(tm_dv, ap + aoff, bdo + 128 * k, idesc_kv, (i > 0 || k > 0) ? 1u : 0u);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint64_t aoff = (uint64_t)((k >> 2) * (FbSmem::TILE >> 4) + (k & 3) * 2);
+          umma_ss(tm_dk, ads + aoff, bq + 128 * k, idesc_kv, (i > 0 || k > 0) ? 1u : 0u);
+        }
+        // dQ_i[q, hd] = sum_keys dS[q, key] K[key, hd]: A = dS^T tile read MN-major (M = q: atoms 16 KiB apart), K = keys
+        mbar_wait(&dq_empty[i & 1], ((i >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint64_t ads_mn = umma_desc_sw128(sds, FbSmem::TILE, 1024);
+        const uint64_t bk = umma_desc_sw128(sk, 128 * 128, 1024);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) umma_ss(tm_dq[i & 1], ads_mn + 128 * k, bk + 128 * k, idesc_q, k > 0 ? 1u : 0u);
+        umma_commit(&dq_full[i & 1]);
+        umma_commit(pds_empty);
+        umma_commit(&qdo_empty[st]);
+      }
+      umma_commit(acc_full);
+    }
+    __syncwarp();
+  } else {
+    const int cw = warp - 2;                 // 0..7
+    const int q4 = warp & 3;                 // TMEM lane quarter
+    const int g = cw >> 2;                   // column half
+    const int lane = (int)lane_id();
+    const int r = q4 * 32 + lane;            // key row (S^T/dP^T) or query row (dQ) inside the tile
+    const uint32_t lane_sel = (uint32_t)(q4 * 32) << 16;
+    uint8_t* prow = smem + FbSmem::OFF_P + g * FbSmem::TILE + r * 128;
+    uint8_t* dsrow = smem + FbSmem::OFF_DS + g * FbSmem::TILE + r * 128;
+    auto reduce_dq = [&](int i) {
+      mbar_wait(&dq_full[i & 1], (i >> 1) & 1);
+      tc_fence_after();
+      uint32_t t[32];
+      tmem_ld_32x32b_x32(tm_dq[i & 1] + lane_sel + 32 * g, t);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&dq_empty[i & 1]);
+      const int qi = i * 128 + r;
+      if (qi < p.N) {
+        float* dst = p.dq_acc + ((long long)b * p.N + qi) * D + h * kHD + 32 * g;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          red_add_v4_f32(dst + 4 * c, __uint_as_float(t[4 * c]), __uint_as_float(t[4 * c + 1]), __uint_as_float(t[4 * c + 2]),
+                         __uint_as_float(t[4 * c + 3]));
+      }
+    };
+    for (int i = 0; i < T; ++i) {
+      const int st = i & 1;
+      const float* lse_s = reinterpret_cast<const float*>(smem + FbSmem::OFF_STAT + st * 1024) + 64 * g;
+      const float* del_s = lse_s + 128;
+      mbar_wait(&qdo_full[st], (i >> 1) & 1);      // lse2 / delta of this query tile have landed
+      mbar_wait(sdp_full, i & 1);
+      tc_fence_after();
+      uint32_t pp[32], dd[32];                     // packed bf16x2: P^T and dS^T for this thread's 64 queries
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t sv_[32], dp_[32];
+        tmem_ld_32x32b_x32(tm_s + lane_sel + 64 * g + 32 * c, sv_);
+        tmem_ld_32x32b_x32(tm_dp + lane_sel + 64 * g + 32 * c, dp_);
+        tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const float2 ls = *reinterpret_cast<const float2*>(lse_s + 32 * c + 2 * k);
+          const float2 dl = *reinterpret_cast<const float2*>(del_s + 32 * c + 2 * k);
+          const float p0 = fast_exp2(fmaf(__uint_as_float(sv_[2 * k]), p.scale_log2, -ls.x));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(sv_[2 * k + 1]), p.scale_log2, -ls.y));
+          pp[16 * c + k] = pack_bf16(p0, p1);
+          dd[16 * c + k] = pack_bf16(p0 * (__uint_as_float(dp_[2 * k]) - dl.x), p1 * (__uint_as_float(dp_[2 * k + 1]) - dl.y));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sdp_empty);
+      mbar_wait(pds_empty, (i & 1) ^ 1);           // the MMAs of tile i-1 have finished reading P^T / dS^T
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int off = (c ^ (r & 7)) << 4;
+        *reinterpret_cast<uint4*>(prow + off) = make_uint4(pp[4 * c], pp[4 * c + 1], pp[4 * c + 2], pp[4 * c + 3]);
+        *reinterpret_cast<uint4*>(dsrow + off) = make_uint4(dd[4 * c], dd[4 * c + 1], dd[4 * c + 2], dd[4 * c + 3]);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pds_full);
+      if (i > 0) reduce_dq(i - 1);
+    }
+    reduce_dq(T - 1);
+    // epilogue: dK (scaled) and dV rows of this key tile
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const int ki = k0 + r;
+    {
+      uint32_t t0[32], t1[32];
+      const uint32_t src = (g == 0 ? tm_dk : tm_dv) + lane_sel;
+      tmem_ld_32x32b_x32(src, t0);
+      tmem_ld_32x32b_x32(src + 32, t1);
+      tmem_ld_wait();
+      if (ki < p.N) {
+        const float sc = g == 0 ? p.scale : 1.0f;
+        uint4* dst = reinterpret_cast<uint4*>(p.dqkv + ((long long)b * p.N + ki) * p.ld + (g == 0 ? D : 2 * D) + h * kHD);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          dst[c] = make_uint4(pack_bf16(sc * __uint_as_float(t0[8 * c]), sc * __uint_as_float(t0[8 * c + 1])),
+                              pack_bf16(sc * __uint_as_float(t0[8 * c + 2]), sc * __uint_as_float(t0[8 * c + 3])),
+                              pack_bf16(sc * __uint_as_float(t0[8 * c + 4]), sc * __uint_as_float(t0[8 * c + 5])),
+                              pack_bf16(sc * __uint_as_float(t0[8 * c + 6]), sc * __uint_as_float(t0[8 * c + 7])));
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          dst[4 + c] = make_uint4(pack_bf16(sc * __uint_as_float(t1[8 * c]), sc * __uint_as_float(t1[8 * c + 1])),
+                                  pack_bf16(sc * __uint_as_float(t1[8 * c + 2]), sc * __uint_as_float(t1[8 * c + 3])),
+                                  pack_bf16(sc * __uint_as_float(t1[8 * c + 4]), sc * __uint_as_float(t1[8 * c + 5])),
+                                  pack_bf16(sc * __uint_as_float(t1[8 * c + 6]), sc * __uint_as_float(t1[8 * c + 7])));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem);
+  }
+}
+
+// delta[b,h,q] = sum_d dO[b,q,h,d] * O[b,q,h,d]   (rows q in [N, Npad) are written as 0)
+__global__ void __launch_bounds__(256) flash_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout,
+                                                          float* __restrict__ delta, int B, int N, int H, int Npad) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (b, q, h) with h fastest
+  const long long total = (long long)B * Npad * H;
+  if (idx >= total) return;
+  const int h = (int)(idx % H);
+  const long long bq = idx / H;
+  const int q = (int)(bq % Npad), b = (int)(bq / Npad);
+  float s = 0.f;
+  if (q < N) {
+    const long long off = ((long long)b * N + q) * (H * kHD) + h * kHD;
+    const uint4* po = reinterpret_cast<const uint4*>(o + off);
+    const uint4* pd = reinterpret_cast<const uint4*>(dout + off);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const uint4 a = __ldg(po + c), d = __ldg(pd + c);
+      const float2 a0 = unpack_bf16(a.x), a1 = unpack_bf16(a.y), a2 = unpack_bf16(a.z), a3 = unpack_bf16(a.w);
+      const float2 d0 = unpack_bf16(d.x), d1 = unpack_bf16(d.y), d2 = unpack_bf16(d.z), d3 = unpack_bf16(d.w);
+      s += a0.x * d0.x + a0.y * d0.y + a1.x * d1.x + a1.y * d1.y + a2.x * d2.x + a2.y * d2.y + a3.x * d3.x + a3.y * d3.y;
+    }
+  }
+  delta[((long long)b * H + h) * Npad + q] = s;
+}
+
+// dqkv[:, 0:D] = bf16(scale * dq_acc)
+__global__ void __launch_bounds__(256) flash_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dqkv,
+                                                               long long rows, int D, long long ld, float scale) {
+  const long long n8 = rows * (D / 8);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / (D / 8);
+    const int c8 = (int)(i % (D / 8));
+    const float4 a = __ldcs(reinterpret_cast<const float4*>(acc + row * D + c8 * 8));
+    const float4 c = __ldcs(reinterpret_cast<const float4*>(acc + row * D + c8 * 8) + 1);
+    *reinterpret_cast<uint4*>(dqkv + row * ld + c8 * 8) =
+        make_uint4(pack_bf16(a.x * scale, a.y * scale), pack_bf16(a.z * scale, a.w * scale), pack_bf16(c.x * scale, c.y * scale),
+                   pack_bf16(c.z * scale, c.w * scale));
+  }
+}
+
+static int make_qkv_tmap(CUtensorMap* tm, const void* qkv, int B, int N, int D3, uint32_t box_rows) {
+  const uint64_t dims[3] = {(uint64_t)D3, (uint64_t)N, (uint64_t)B};
+  const uint64_t str[2] = {(uint64_t)D3 * 2, (uint64_t)N * D3 * 2};
+  const uint32_t box[3] = {64, box_rows, 1};
+  return make_tmap_nd(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, qkv, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+}  // namespace dv
+
+extern "C" int devias_flash_attn_fwd(const void* qkv, void* out, float* lse2, int batch, int seq, int heads, int head_dim,
+                                     float scale, void* stream) {
+  using namespace dv;
+  DV_REQUIRE(qkv && out, "null pointer");
+  DV_REQUIRE(head_dim == 64, "head_dim 64 only (ViT-B/16)");
+  DV_REQUIRE(batch > 0 && seq > 0 && heads > 0, "empty problem");
+  const int D = heads * kHD;
+  CUtensorMap tmQ, tmKV;
+  int rc = make_qkv_tmap(&tmQ, qkv, batch, seq, 3 * D, kQT);
+  if (rc) return rc;
+  rc = make_qkv_tmap(&tmKV, qkv, batch, seq, 3 * D, kKT);
+  if (rc) return rc;
+  static bool attr_done = false;
+  if (!attr_done) {
+    DV_CHECK_CUDA(cudaFuncSetAttribute(flash_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FaSmem::BYTES));
+    attr_done = true;
+  }
+  FaParams p{batch, seq, heads, (seq + 127) / 128 * 128, scale * 1.4426950408889634f, static_cast<__nv_bfloat16*>(out),
+             (long long)D, lse2};
+  const int q_tiles = (seq + kQT - 1) / kQT;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int prof = prof_begin(DEVIAS_PROF_ATTN, 4.0 * batch * heads * (double)seq * seq * kHD, s);
+  flash_fwd_kernel<<<batch * heads * q_tiles, kFaThreads, FaSmem::BYTES, s>>>(tmQ, tmKV, p);
+  prof_end(prof, s);
+  DV_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return DEVIAS_OK;
+}
+
+extern "C" int devias_flash_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse2, void* dqkv,
+                                     float* delta_ws, float* dq_ws, int batch, int seq, int heads, int head_dim, float scale,
+                                     void* stream) {
+  using namespace dv;
+  DV_REQUIRE(qkv && out && dout && lse2 && dqkv && delta_ws && dq_ws, "null pointer");
+  DV_REQUIRE(head_dim == 64, "head_dim 64 only (ViT-B/16)");
+  DV_REQUIRE(batch > 0 && seq > 0 && heads > 0, "empty problem");
+  const int D = heads * kHD;
+  const int Npad = (seq + 127) / 128 * 128;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CUtensorMap tmQKV, tmDO;
+  int rc = make_qkv_tmap(&tmQKV, qkv, batch, seq, 3 * D, 128);
+  if (rc) return rc;
+  rc = make_qkv_tmap(&tmDO, dout, batch, seq, D, 128);
+  if (rc) return rc;
+  static bool attr_done = false;
+  if (!attr_done) {
+    DV_CHECK_CUDA(cudaFuncSetAttribute(flash_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FbSmem::BYTES));
+    attr_done = true;
+  }
+  DV_CHECK_CUDA(cudaMemsetAsync(dq_ws, 0, (size_t)batch * seq * D * sizeof(float), s));
+  {
+    const long long total = (long long)batch * Npad * heads;
+    flash_delta_kernel<<<(int)((total + 255) / 256), 256, 0, s>>>(static_cast<const __nv_bfloat16*>(out),
+                                                                  static_cast<const __nv_bfloat16*>(dout), delta_ws, batch, seq,
+                                                                  heads, Npad);
+  }
+  FbParams p{batch, seq, heads, Npad, scale, scale * 1.4426950408889634f, lse2, delta_ws, dq_ws,
+             static_cast<__nv_bfloat16*>(dqkv), (long long)3 * D};
+  const int k_tiles = (seq + 127) / 128;
+  const int prof = prof_begin(DEVIAS_PROF_ATTN, 10.0 * batch * heads * (double)seq * seq * kHD, s);
+  flash_bwd_kernel<<<batch * heads * k_tiles, kBwdThreads, FbSmem::BYTES, s>>>(tmQKV, tmDO, p);
+  prof_end(prof, s);
+  {
+    const long long n8 = (long long)batch * seq * (D / 8);
+    long long blocks = (n8 + 255) / 256;
+    if (blocks > sm_count() * 16) blocks = sm_count() * 16;
+    flash_dq_convert_kernel<<<(int)blocks, 256, 0, s>>>(dq_ws, static_cast<__nv_bfloat16*>(dqkv), (long long)batch * seq, D,
+                                                        (long long)3 * D, scale);
+  }
+  DV_CHECK_CUDA(cudaGetLastError());
+  count_launch(3);
+  return DEVIAS_OK;
+}

@@ -1,0 +1,290 @@
+// Streaming slot attention (agg_block/attention.py:120-141 under PreNorm :32-40) in the folded form of
+// devias_b200/slot_attention.py: per layer the 1568 x 768 context tokens of a clip are read from HBM exactly once.
+//
+//   sim[sh, j] = r_j * (g[sh] . t_j - mu_j * G[sh]) + c0[sh]        (sh = head * S + slot;  mu_j, r_j = LayerNorm stats of t_j)
+//   a = softmax over the S slots of each head;   A[sh] = sum_j a,   U[sh] = sum_j (a r_j) t_j,   m[sh] = sum_j a r_j mu_j
+//
+// One CTA streams a contiguous range of 16-token tiles of one clip through a TMA ring (128B-swizzled boxes of
+// 32 floats x 16 tokens, so both access patterns below are bank-conflict free):
+//   phase 1 (8 warps)  : lane <-> token, warp <-> 96-wide channel slice: HS dot products + shifted LayerNorm moments
+//   phase 1b (warp 0)  : combine the slices, LayerNorm stats, logits, slot-axis softmax, weights
+//   phase 2 (6 warps)  : thread <-> 4 channels: U[sh][d] += w[sh][j] * t[j][d]
+// Partial U / m / A of the CTA are flushed with red.global.add (few CTAs per clip).  fp32 FFMA throughout: the 1e-5
+// parity budget of BASELINE.json rules out tf32/bf16 tensor-core products for the fp32 path.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace dv {
+
+constexpr int kSD = 768;          // channels
+constexpr int kST = 16;           // tokens per tile
+constexpr int kSBoxes = kSD / 32; // 24 TMA boxes (32 floats) per tile
+constexpr int kSTileBytes = kST * kSD * 4;   // 48 KiB
+constexpr int kSlotThreads = 256;
+
+template <int HS>
+struct SlotCfg {
+  static constexpr int STAGES = (HS <= 16) ? 3 : 2;
+  static constexpr int OFF_TILE = 0;
+  static constexpr int OFF_G = STAGES * kSTileBytes;                 // g[HS][768] fp32
+  static constexpr int OFF_PART = OFF_G + HS * kSD * 4;              // partial[8 warps][16 tokens][HS + 2]
+  static constexpr int PART_BYTES = 8 * kST * (HS + 2) * 4;
+  static constexpr int OFF_W = OFF_PART + PART_BYTES;                // w[16 tokens][HS]  (a * r)
+  static constexpr int OFF_ACC = OFF_W + kST * HS * 4;               // running A / m partials [2][16 tokens][HS]
+  static constexpr int OFF_BAR = OFF_ACC + 2 * kST * HS * 4;
+  static constexpr int BYTES = OFF_BAR + 64 + 1024;
+};
+
+struct SlotParams {
+  int B, N, S;                 // HS = 4 * S
+  int tiles_per_cta, tiles_per_clip;
+  const float* g;              // [B, HS, 768]
+  const float* G;              // [B, HS]
+  const float* c0;             // [B, HS]
+  float* U;                    // [B, HS, 768]  (+=)
+  float* m;                    // [B, HS]       (+=)
+  float* A;                    // [B, HS]       (+=)
+  float* attn;                 // [B, HS, N] or null
+  float* mu;                   // [B, N] or null (LayerNorm stats written for the backward)
+  float* rstd;                 // [B, N] or null
+  float eps;
+};
+
+// address of the 16-byte chunk holding channels [4*c4, 4*c4+4) of token `tok` inside a swizzled tile
+__device__ __forceinline__ const float4* tile_chunk(const uint8_t* tile, int tok, int c4) {
+  const int box = c4 >> 3, chunk = c4 & 7;
+  return reinterpret_cast<const float4*>(tile + box * (kST * 128) + tok * 128 + ((chunk ^ (tok & 7)) << 4));
+}
+
+template <int HS>
+__global__ void __launch_bounds__(kSlotThreads, 1)
+slot_stream_fwd_kernel(const __grid_constant__ CUtensorMap tmTok, const SlotParams p) {
+  using Cfg = SlotCfg<HS>;
+  constexpr int S = HS / 4;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* g_s = reinterpret_cast<float*>(smem + Cfg::OFF_G);
+  float* part = reinterpret_cast<float*>(smem + Cfg::OFF_PART);
+  float* w_s = reinterpret_cast<float*>(smem + Cfg::OFF_W);
+  float* accA = reinterpret_cast<float*>(smem + Cfg::OFF_ACC);   // [16][HS]
+  float* accM = accA + kST * HS;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.y;
+  const int tile0 = blockIdx.x * p.tiles_per_cta;
+  const int ntiles = min(p.tiles_per_cta, p.tiles_per_clip - tile0);
+  if (ntiles <= 0) return;
+
+  if (tid == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) mbar_init(&full[s], 1);
+    fence_barrier_init();
+  }
+  // g of this clip -> smem (plain coalesced loads; 24..96 KiB once per CTA)
+  {
+    const float4* src = reinterpret_cast<const float4*>(p.g + (long long)b * HS * kSD);
+    float4* dst = reinterpret_cast<float4*>(g_s);
+    for (int i = tid; i < HS * kSD / 4; i += kSlotThreads) dst[i] = __ldg(src + i);
+    for (int i = tid; i < 2 * kST * HS; i += kSlotThreads) accA[i] = 0.f;
+  }
+  __syncthreads();
+
+  auto issue = [&](int it) {   // one elected thread: 24 boxes of 32 floats x 16 tokens
+    const int st = it % Cfg::STAGES;
+    mbar_arrive_expect_tx(&full[st], kSTileBytes);
+    uint8_t* dst = smem + Cfg::OFF_TILE + st * kSTileBytes;
+    const int tok0 = (tile0 + it) * kST;
+#pragma unroll 1
+    for (int bx = 0; bx < kSBoxes; ++bx) tma_load_3d(dst + bx * (kST * 128), &tmTok, &full[st], bx * 32, tok0, b);
+  };
+  if (tid == 0) {
+    for (int it = 0; it < Cfg::STAGES - 1 && it < ntiles; ++it) issue(it);
+  }
+
+  // phase-2 accumulators: thread t < 192 owns channels [4t, 4t+4) for every sh
+  float4 acc[HS];
+#pragma unroll
+  for (int i = 0; i < HS; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float* Gs = p.G + b * HS;
+  const float* c0s = p.c0 + b * HS;
+
+  const int tok_l = lane & 15, half = lane >> 4;
+  const int slice = warp * 2 + half;                  // 16 channel slices of 48
+  for (int it = 0; it < ntiles; ++it) {
+    const int st = it % Cfg::STAGES;
+    // keep the ring full: the stage being refilled was consumed in iteration it-1 (all threads passed its last barrier)
+    if (tid == 0 && it + Cfg::STAGES - 1 < ntiles) issue(it + Cfg::STAGES - 1);
+    mbar_wait(&full[st], (it / Cfg::STAGES) & 1);
+    const uint8_t* tile = smem + Cfg::OFF_TILE + st * kSTileBytes;
+    const int tok_base = (tile0 + it) * kST;
+
+    // ---------------- phase 1: partial dots over this lane's 48 channels of token tok_l
+    {
+      float dot[HS];
+#pragma unroll
+      for (int i = 0; i < HS; ++i) dot[i] = 0.f;
+      const float x0 = tile_chunk(tile, tok_l, 0)->x;   // shift for the one-pass moments (same for all slices of a token)
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll 4
+      for (int c = 0; c < 12; ++c) {
+        const int c4 = slice * 12 + c;
+        const float4 t = *tile_chunk(tile, tok_l, c4);
+        const float a0 = t.x - x0, a1 = t.y - x0, a2 = t.z - x0, a3 = t.w - x0;
+        s1 += (a0 + a1) + (a2 + a3);
+        s2 = fmaf(a0, a0, fmaf(a1, a1, fmaf(a2, a2, fmaf(a3, a3, s2))));
+#pragma unroll
+        for (int i = 0; i < HS; ++i) {
+          const float4 gv = *reinterpret_cast<const float4*>(g_s + i * kSD + c4 * 4);
+          dot[i] = fmaf(t.x, gv.x, fmaf(t.y, gv.y, fmaf(t.z, gv.z, fmaf(t.w, gv.w, dot[i]))));
+        }
+      }
+      // combine the two 48-channel halves of this warp, lanes 0..15 publish
+#pragma unroll
+      for (int i = 0; i < HS; ++i) dot[i] += __shfl_xor_sync(0xffffffffu, dot[i], 16);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
+      if (half == 0) {
+        float* pp = part + (warp * kST + tok_l) * (HS + 2);
+#pragma unroll
+        for (int i = 0; i < HS; ++i) pp[i] = dot[i];
+        pp[HS] = s1;
+        pp[HS + 1] = s2;
+      }
+    }
+    __syncthreads();
+    // ---------------- phase 1b: warp 0, lanes 0..15 <-> tokens
+    if (warp == 0 && lane < kST) {
+      float dot[HS];
+#pragma unroll
+      for (int i = 0; i < HS; ++i) dot[i] = 0.f;
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll 4
+      for (int sl = 0; sl < 8; ++sl) {
+        const float* pp = part + (sl * kST + lane) * (HS + 2);
+#pragma unroll
+        for (int i = 0; i < HS; ++i) dot[i] += pp[i];
+        s1 += pp[HS];
+        s2 += pp[HS + 1];
+      }
+      const float x0 = tile_chunk(tile, lane, 0)->x;
+      const float d1 = s1 * (1.0f / kSD);
+      const float mu = x0 + d1;
+      const float var = fmaxf(s2 * (1.0f / kSD) - d1 * d1, 0.f);
+      const float r = rsqrtf(var + p.eps);
+      const int tok = tok_base + lane;
+      const bool valid = tok < p.N;
+      if (valid && p.mu != nullptr) { p.mu[(long long)b * p.N + tok] = mu; p.rstd[(long long)b * p.N + tok] = r; }
+      float a[HS];
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        float mx = -INFINITY;
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          const int i = h * S + s;
+          a[i] = fmaf(r, dot[i] - mu * __ldg(Gs + i), __ldg(c0s + i));
+          mx = fmaxf(mx, a[i]);
+        }
+        float sum = 0.f;
+#pragma unroll
+        for (int s = 0; s < S; ++s) { a[h * S + s] = expf(a[h * S + s] - mx); sum += a[h * S + s]; }
+        const float inv = valid ? 1.0f / sum : 0.f;
+#pragma unroll
+        for (int s = 0; s < S; ++s) a[h * S + s] *= inv;
+      }
+#pragma unroll
+      for (int i = 0; i < HS; ++i) {
+        const float w = a[i] * r;
+        w_s[lane * HS + i] = w;
+        accA[lane * HS + i] += a[i];
+        accM[lane * HS + i] = fmaf(w, mu, accM[lane * HS + i]);
+        if (p.attn != nullptr && valid) p.attn[((long long)b * HS + i) * p.N + tok] = a[i];
+      }
+    }
+    __syncthreads();
+    // ---------------- phase 2: U[sh][4t..4t+3] += w[j][sh] * token_j[4t..4t+3]
+    if (tid < kSD / 4) {
+#pragma unroll 4
+      for (int j = 0; j < kST; ++j) {
+        const float4 t = *tile_chunk(tile, j, tid);
+#pragma unroll
+        for (int i4 = 0; i4 < HS / 4; ++i4) {
+          const float4 w = *reinterpret_cast<const float4*>(w_s + j * HS + 4 * i4);
+          float4& a0 = acc[4 * i4]; float4& a1 = acc[4 * i4 + 1]; float4& a2 = acc[4 * i4 + 2]; float4& a3 = acc[4 * i4 + 3];
+          a0.x = fmaf(w.x, t.x, a0.x); a0.y = fmaf(w.x, t.y, a0.y); a0.z = fmaf(w.x, t.z, a0.z); a0.w = fmaf(w.x, t.w, a0.w);
+          a1.x = fmaf(w.y, t.x, a1.x); a1.y = fmaf(w.y, t.y, a1.y); a1.z = fmaf(w.y, t.z, a1.z); a1.w = fmaf(w.y, t.w, a1.w);
+          a2.x = fmaf(w.z, t.x, a2.x); a2.y = fmaf(w.z, t.y, a2.y); a2.z = fmaf(w.z, t.z, a2.z); a2.w = fmaf(w.z, t.w, a2.w);
+          a3.x = fmaf(w.w, t.x, a3.x); a3.y = fmaf(w.w, t.y, a3.y); a3.z = fmaf(w.w, t.z, a3.z); a3.w = fmaf(w.w, t.w, a3.w);
+        }
+      }
+    }
+    __syncthreads();   // tile + w_s + part fully consumed: the stage may be refilled
+  }
+  // ---------------- flush partials
+  if (tid < kSD / 4) {
+    float* dst = p.U + (long long)b * HS * kSD + tid * 4;
+#pragma unroll
+    for (int i = 0; i < HS; ++i) red_add_v4_f32(dst + i * kSD, acc[i].x, acc[i].y, acc[i].z, acc[i].w);
+  }
+  if (tid < HS) {   // the loop's final barrier made warp 0's running sums visible
+    float a = 0.f, mm = 0.f;
+#pragma unroll
+    for (int j = 0; j < kST; ++j) { a += accA[j * HS + tid]; mm += accM[j * HS + tid]; }
+    atomicAdd(p.A + b * HS + tid, a);
+    atomicAdd(p.m + b * HS + tid, mm);
+  }
+}
+
+static int make_token_tmap(CUtensorMap* tm, const float* tokens, int B, int N) {
+  const uint64_t dims[3] = {(uint64_t)kSD, (uint64_t)N, (uint64_t)B};
+  const uint64_t str[2] = {(uint64_t)kSD * 4, (uint64_t)N * kSD * 4};
+  const uint32_t box[3] = {32, kST, 1};
+  return make_tmap_nd(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, tokens, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+template <int HS>
+static int launch_slot_fwd(const CUtensorMap& tm, const SlotParams& p, int splits, cudaStream_t s) {
+  using Cfg = SlotCfg<HS>;
+  auto kern = slot_stream_fwd_kernel<HS>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    DV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::BYTES));
+    attr_done = true;
+  }
+  const double bytes = (double)p.B * p.N * kSD * 4 + (p.attn ? (double)p.B * HS * p.N * 4 : 0.0);
+  const int prof = prof_begin(DEVIAS_PROF_SLOT, bytes, s);
+  kern<<<dim3(splits, p.B), kSlotThreads, Cfg::BYTES, s>>>(tm, p);
+  prof_end(prof, s);
+  DV_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return DEVIAS_OK;
+}
+
+}  // namespace dv
+
+extern "C" int devias_slot_stream_fwd(const float* tokens, const float* g, const float* G, const float* c0, float* U, float* m,
+                                      float* A, float* attn, float* mu, float* rstd, int batch, int n_tokens, int dim,
+                                      int num_slots, float eps, void* stream) {
+  using namespace dv;
+  DV_REQUIRE(tokens && g && G && c0 && U && m && A, "null pointer");
+  DV_REQUIRE(dim == kSD, "token dim must be 768");
+  DV_REQUIRE(num_slots == 2 || num_slots == 4 || num_slots == 8, "num_slots must be 2, 4 or 8 (4 heads x S query vectors)");
+  DV_REQUIRE((mu == nullptr) == (rstd == nullptr), "mu and rstd go together");
+  DV_REQUIRE(batch > 0 && n_tokens > 0, "empty problem");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CUtensorMap tm;
+  int rc = make_token_tmap(&tm, tokens, batch, n_tokens);
+  if (rc) return rc;
+  const int tiles = (n_tokens + kST - 1) / kST;
+  // enough CTAs for ~2 waves over the SMs, but at least 4 tiles each so the per-CTA flush stays cheap
+  int splits = (2 * sm_count() + batch - 1) / batch;
+  if (splits > (tiles + 3) / 4) splits = (tiles + 3) / 4;
+  if (splits < 1) splits = 1;
+  const int per = (tiles + splits - 1) / splits;
+  splits = (tiles + per - 1) / per;
+  SlotParams p{batch, n_tokens, num_slots, per, tiles, g, G, c0, U, m, A, attn, mu, rstd, eps};
+  switch (num_slots) {
+    case 2: return launch_slot_fwd<8>(tm, p, splits, s);
+    case 4: return launch_slot_fwd<16>(tm, p, splits, s);
+    default: return launch_slot_fwd<32>(tm, p, splits, s);
+  }
+}

@@ -140,3 +140,50 @@ def patchify(clip: torch.Tensor):
     rc = _lib.lib().devias_patchify(clip.data_ptr(), _DT[clip.dtype], out.data_ptr(), B, C, T, H, W, _stream())
     _lib.check(rc, 'patchify')
     return out
+
+
+def flash_attn_fwd(qkv: torch.Tensor, B: int, N: int, H: int, need_lse=True):
+    """qkv bf16 [B*N, 3*H*64] -> (out bf16 [B*N, H*64], lse2 fp32 [B, H, Npad] | None)"""
+    _need_cuda(qkv)
+    assert qkv.dtype == torch.bfloat16 and qkv.is_contiguous() and qkv.shape == (B * N, 3 * H * 64)
+    out = torch.empty(B * N, H * 64, device=qkv.device, dtype=torch.bfloat16)
+    npad = (N + 127) // 128 * 128
+    lse2 = torch.empty(B, H, npad, device=qkv.device, dtype=torch.float32) if need_lse else None
+    rc = _lib.lib().devias_flash_attn_fwd(qkv.data_ptr(), out.data_ptr(), _ptr(lse2), B, N, H, 64, 0.125, _stream())
+    _lib.check(rc, 'flash_attn_fwd')
+    return out, lse2
+
+
+def flash_attn_bwd(qkv, out, dout, lse2, B: int, N: int, H: int):
+    """-> dqkv bf16 [B*N, 3*H*64]"""
+    _need_cuda(qkv, out, dout, lse2)
+    assert dout.dtype == torch.bfloat16 and dout.is_contiguous() and out.is_contiguous() and qkv.is_contiguous()
+    npad = (N + 127) // 128 * 128
+    dqkv = torch.empty_like(qkv)
+    delta = torch.empty(B * H * npad, device=qkv.device, dtype=torch.float32)
+    dq = torch.empty(B * N * H * 64, device=qkv.device, dtype=torch.float32)
+    rc = _lib.lib().devias_flash_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse2.data_ptr(), dqkv.data_ptr(),
+                                          delta.data_ptr(), dq.data_ptr(), B, N, H, 64, 0.125, _stream())
+    _lib.check(rc, 'flash_attn_bwd')
+    return dqkv
+
+
+def slot_stream_fwd(tokens, g, G, c0, want_attn=True, want_stats=True, eps=1e-5):
+    """tokens fp32 [B,N,768]; g [B,HS,768]; G,c0 [B,HS] -> U [B,HS,768], m, A [B,HS], attn [B,HS,N]|None, mu, rstd [B,N]|None"""
+    _need_cuda(tokens, g, G, c0)
+    assert tokens.dtype == torch.float32 and tokens.is_contiguous() and g.is_contiguous() and G.is_contiguous() and c0.is_contiguous()
+    B, N, D = tokens.shape
+    HS = g.shape[1]
+    dev = tokens.device
+    acc = torch.zeros(B, HS, D + 2, device=dev, dtype=torch.float32)   # one memset for U | m | A
+    U = torch.zeros(B, HS, D, device=dev, dtype=torch.float32)
+    mA = torch.zeros(2, B, HS, device=dev, dtype=torch.float32)
+    del acc
+    attn = torch.empty(B, HS, N, device=dev, dtype=torch.float32) if want_attn else None
+    mu = torch.empty(B, N, device=dev, dtype=torch.float32) if want_stats else None
+    rstd = torch.empty(B, N, device=dev, dtype=torch.float32) if want_stats else None
+    rc = _lib.lib().devias_slot_stream_fwd(tokens.data_ptr(), g.data_ptr(), G.data_ptr(), c0.data_ptr(), U.data_ptr(),
+                                           mA[0].data_ptr(), mA[1].data_ptr(), _ptr(attn), _ptr(mu), _ptr(rstd), B, N, D, HS // 4,
+                                           float(eps), _stream())
+    _lib.check(rc, 'slot_stream_fwd')
+    return U, mA[0], mA[1], attn, mu, rstd

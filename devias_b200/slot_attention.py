@@ -30,7 +30,7 @@ def token_stats(tokens: torch.Tensor, eps: float = 1e-5):
 def slot_stream_torch(tokens, mu, r, g, G, c0):
     """INTERIM torch evaluation of the streaming step (same contract as the CUDA kernel):
     tokens [B,N,D]; mu,r [B,N]; g [B,HS,D]; G,c0 [B,HS]  ->  U [B,HS,D], m [B,HS], A [B,HS], a [B,HS,N]"""
-    t = tokens.float()
+    t = tokens if tokens.dtype == torch.float64 else tokens.float()
     B, HS, D = g.shape
     S = HS // HEADS
     dots = torch.bmm(g, t.transpose(1, 2))                                   # [B,HS,N]

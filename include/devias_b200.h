@@ -66,6 +66,30 @@ int devias_gemm_bf16(const void* a, int64_t lda, int a_mn_major, const void* b, 
                      const void* aux, int64_t ldaux, int aux_row_mod, const float* row_scale, int rows_per_scale,
                      int split_k, void* stream);
 
+/* ---- fused softmax attention of the encoder (head_dim 64) ------------------------------------------
+ * qkv: packed bf16 [batch*seq, 3*heads*64] exactly as produced by the qkv GEMM (q | k | v column blocks, head-major inside
+ * each).  out: bf16 [batch*seq, heads*64].  out = softmax(scale * q k^T) v per (clip, head); replaces
+ * model/modeling_slot.py:102-112 (q*scale, q@k^T, softmax, attn@v, transpose/reshape) without materialising the
+ * [12, seq, seq] probabilities.  lse2: fp32 [batch, heads, seq_pad] (seq_pad = seq rounded up to 128), log2-domain
+ * log-sum-exp kept for the backward (may be NULL for inference).
+ * Backward: dqkv bf16 [batch*seq, 3*heads*64] from dout; delta_ws fp32 [batch*heads*seq_pad] and dq_ws fp32
+ * [batch*seq*heads*64] are caller-provided scratch buffers (dq_ws is zeroed by the call). */
+int devias_flash_attn_fwd(const void* qkv, void* out, float* lse2, int batch, int seq, int heads, int head_dim, float scale,
+                          void* stream);
+int devias_flash_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse2, void* dqkv, float* delta_ws,
+                          float* dq_ws, int batch, int seq, int heads, int head_dim, float scale, void* stream);
+
+/* ---- streaming slot attention (folded form; devias_b200/slot_attention.py) ----------------------------
+ * One pass over the context tokens of every clip, replacing per layer: LayerNorm(context) + to_k + to_v + q k^T + slot-axis
+ * softmax + token-axis renormalisation + attn v of agg_block/attention.py:32-40,120-141.
+ *   tokens fp32 [batch, n_tokens, 768]; g fp32 [batch, 4*S, 768]; G, c0 fp32 [batch, 4*S]   (sh = head*S + slot)
+ *   U [batch, 4*S, 768], m, A [batch, 4*S] are ACCUMULATED (+=; pass zero-filled buffers)
+ *   attn [batch, 4*S, n_tokens] (= the reference's sim_distill in '(b h) s n' order) or NULL
+ *   mu, rstd [batch, n_tokens]: LayerNorm statistics of the tokens, written when non-NULL (needed by the backward). */
+int devias_slot_stream_fwd(const float* tokens, const float* g, const float* G, const float* c0, float* U, float* m, float* A,
+                           float* attn, float* mu, float* rstd, int batch, int n_tokens, int dim, int num_slots, float eps,
+                           void* stream);
+
 /* dtype ids for entry points that accept several input element types */
 #define DEVIAS_DTYPE_F32 0
 #define DEVIAS_DTYPE_BF16 1
