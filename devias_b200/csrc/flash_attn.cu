@@ -8,6 +8,8 @@
 //   warps 2..5  : softmax        (thread = query row: TMEM -> registers, online max/sum in the exp2 domain, P_j -> bf16 ->
 //                                 128B-swizzled smem as the A operand of the second MMA, running O in registers)
 // Backward kernels live below (dQ / dK / dV with recomputed probabilities).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -146,7 +148,7 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     float o[kHD];
 #pragma unroll
     for (int i = 0; i < kHD; ++i) o[i] = 0.f;
-    uint8_t* p_row_base = smem + FaSmem::OFF_P + r * 128;
+    const uint32_t p_row_base = smem_u32(smem + FaSmem::OFF_P + r * 128);
     for (int j = 0; j < T; ++j) {
       mbar_wait(&s_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
@@ -158,37 +160,37 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[j & 1]);
       const int valid = p.N - j * kKT;               // keys valid in this tile (>= 64 except the last)
+      if (valid < kKT) {                             // warp-uniform: only the ragged last tile masks
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (i >= valid) s0[i] = 0xff800000u;       // -inf
+          if (i + 32 >= valid) s1[i] = 0xff800000u;
+        }
+      }
       float mx = -INFINITY;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        float a = __uint_as_float(s0[i]) * p.scale_log2, c = __uint_as_float(s1[i]) * p.scale_log2;
-        if (i >= valid) a = -INFINITY;
-        if (i + 32 >= valid) c = -INFINITY;
-        s0[i] = __float_as_uint(a); s1[i] = __float_as_uint(c);
-        mx = fmaxf(mx, fmaxf(a, c));
-      }
-      const float m_new = fmaxf(m, mx);
+      for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(s0[i]), __uint_as_float(s1[i])));
+      const float m_new = fmaxf(m, mx * p.scale_log2);   // scale > 0: max(c s) = c max(s)
       const float alpha = fast_exp2(m - m_new);
       m = m_new;
       // P_j -> smem (K-major, 128B swizzle: 16-byte chunk c of row r lands at chunk c ^ (r & 7))
       mbar_wait(&p_empty[j & 1], ((j >> 1) & 1) ^ 1);
-      uint8_t* prow = p_row_base + (j & 1) * FaSmem::P_BYTES;
+      const uint32_t prow = p_row_base + (j & 1) * FaSmem::P_BYTES;
       float sum = 0.f;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         float e[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { e[i] = fast_exp2(__uint_as_float(s0[8 * c + i]) - m_new); sum += e[i]; }
-        *reinterpret_cast<uint4*>(prow + ((c ^ (r & 7)) << 4)) =
-            make_uint4(pack_bf16(e[0], e[1]), pack_bf16(e[2], e[3]), pack_bf16(e[4], e[5]), pack_bf16(e[6], e[7]));
+        for (int i = 0; i < 8; ++i) { e[i] = fast_exp2(fmaf(__uint_as_float(s0[8 * c + i]), p.scale_log2, -m_new)); sum += e[i]; }
+        sts128(prow + ((c ^ (r & 7)) << 4), pack_bf16(e[0], e[1]), pack_bf16(e[2], e[3]), pack_bf16(e[4], e[5]), pack_bf16(e[6], e[7]));
       }
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         float e[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { e[i] = fast_exp2(__uint_as_float(s1[8 * c + i]) - m_new); sum += e[i]; }
-        *reinterpret_cast<uint4*>(prow + (((c + 4) ^ (r & 7)) << 4)) =
-            make_uint4(pack_bf16(e[0], e[1]), pack_bf16(e[2], e[3]), pack_bf16(e[4], e[5]), pack_bf16(e[6], e[7]));
+        for (int i = 0; i < 8; ++i) { e[i] = fast_exp2(fmaf(__uint_as_float(s1[8 * c + i]), p.scale_log2, -m_new)); sum += e[i]; }
+        sts128(prow + (((c + 4) ^ (r & 7)) << 4), pack_bf16(e[0], e[1]), pack_bf16(e[2], e[3]), pack_bf16(e[4], e[5]),
+               pack_bf16(e[6], e[7]));
       }
       l = l * alpha + sum;
       fence_proxy_async();
@@ -275,6 +277,7 @@ struct FbParams {
   const float* lse2; const float* delta;   // [B, H, Npad]
   float* dq_acc;                            // [B*N, H*64] fp32, zero-initialised
   __nv_bfloat16* dqkv; long long ld;        // [B*N, 3*H*64]
+  int debug_skip_dq;                        // timing experiments only (DEVIAS_DEBUG_SKIP_DQ=1): drop the dQ reduction
 };
 
 __global__ void __launch_bounds__(kBwdThreads, 1)
@@ -409,8 +412,8 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
     const int lane = (int)lane_id();
     const int r = q4 * 32 + lane;            // key row (S^T/dP^T) or query row (dQ) inside the tile
     const uint32_t lane_sel = (uint32_t)(q4 * 32) << 16;
-    uint8_t* prow = smem + FbSmem::OFF_P + g * FbSmem::TILE + r * 128;
-    uint8_t* dsrow = smem + FbSmem::OFF_DS + g * FbSmem::TILE + r * 128;
+    const uint32_t prow = smem_u32(smem + FbSmem::OFF_P + g * FbSmem::TILE + r * 128);
+    const uint32_t dsrow = smem_u32(smem + FbSmem::OFF_DS + g * FbSmem::TILE + r * 128);
     auto reduce_dq = [&](int i) {
       mbar_wait(&dq_full[i & 1], (i >> 1) & 1);
       tc_fence_after();
@@ -421,7 +424,7 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
       __syncwarp();
       if (lane == 0) mbar_arrive(&dq_empty[i & 1]);
       const int qi = i * 128 + r;
-      if (qi < p.N) {
+      if (qi < p.N && !p.debug_skip_dq) {
         float* dst = p.dq_acc + ((long long)b * p.N + qi) * D + h * kHD + 32 * g;
 #pragma unroll
         for (int c = 0; c < 8; ++c)
@@ -431,8 +434,8 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
     };
     for (int i = 0; i < T; ++i) {
       const int st = i & 1;
-      const float* lse_s = reinterpret_cast<const float*>(smem + FbSmem::OFF_STAT + st * 1024) + 64 * g;
-      const float* del_s = lse_s + 128;
+      const uint32_t lse_s = smem_u32(smem + FbSmem::OFF_STAT + st * 1024) + 256 * g;   // lse2[64 g ..]
+      const uint32_t del_s = lse_s + 512;
       mbar_wait(&qdo_full[st], (i >> 1) & 1);      // lse2 / delta of this query tile have landed
       mbar_wait(sdp_full, i & 1);
       tc_fence_after();
@@ -445,8 +448,8 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         tmem_ld_wait();
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-          const float2 ls = *reinterpret_cast<const float2*>(lse_s + 32 * c + 2 * k);
-          const float2 dl = *reinterpret_cast<const float2*>(del_s + 32 * c + 2 * k);
+          const float2 ls = lds64(lse_s + 4 * (32 * c + 2 * k));
+          const float2 dl = lds64(del_s + 4 * (32 * c + 2 * k));
           const float p0 = fast_exp2(fmaf(__uint_as_float(sv_[2 * k]), p.scale_log2, -ls.x));
           const float p1 = fast_exp2(fmaf(__uint_as_float(sv_[2 * k + 1]), p.scale_log2, -ls.y));
           pp[16 * c + k] = pack_bf16(p0, p1);
@@ -460,8 +463,8 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         const int off = (c ^ (r & 7)) << 4;
-        *reinterpret_cast<uint4*>(prow + off) = make_uint4(pp[4 * c], pp[4 * c + 1], pp[4 * c + 2], pp[4 * c + 3]);
-        *reinterpret_cast<uint4*>(dsrow + off) = make_uint4(dd[4 * c], dd[4 * c + 1], dd[4 * c + 2], dd[4 * c + 3]);
+        sts128(prow + off, pp[4 * c], pp[4 * c + 1], pp[4 * c + 2], pp[4 * c + 3]);
+        sts128(dsrow + off, dd[4 * c], dd[4 * c + 1], dd[4 * c + 2], dd[4 * c + 3]);
       }
       fence_proxy_async();
       __syncwarp();
@@ -611,7 +614,7 @@ extern "C" int devias_flash_attn_bwd(const void* qkv, const void* out, const voi
                                                                   heads, Npad);
   }
   FbParams p{batch, seq, heads, Npad, scale, scale * 1.4426950408889634f, lse2, delta_ws, dq_ws,
-             static_cast<__nv_bfloat16*>(dqkv), (long long)3 * D};
+             static_cast<__nv_bfloat16*>(dqkv), (long long)3 * D, getenv("DEVIAS_DEBUG_SKIP_DQ") != nullptr ? 1 : 0};
   const int k_tiles = (seq + 127) / 128;
   const int prof = prof_begin(DEVIAS_PROF_ATTN, 10.0 * batch * heads * (double)seq * seq * kHD, s);
   flash_bwd_kernel<<<batch * heads * k_tiles, kBwdThreads, FbSmem::BYTES, s>>>(tmQKV, tmDO, p);

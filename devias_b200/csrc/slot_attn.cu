@@ -50,10 +50,10 @@ struct SlotParams {
   float eps;
 };
 
-// address of the 16-byte chunk holding channels [4*c4, 4*c4+4) of token `tok` inside a swizzled tile
-__device__ __forceinline__ const float4* tile_chunk(const uint8_t* tile, int tok, int c4) {
+// shared-space address of the 16-byte chunk holding channels [4*c4, 4*c4+4) of token `tok` inside a swizzled tile
+__device__ __forceinline__ uint32_t tile_chunk(uint32_t tile, int tok, int c4) {
   const int box = c4 >> 3, chunk = c4 & 7;
-  return reinterpret_cast<const float4*>(tile + box * (kST * 128) + tok * 128 + ((chunk ^ (tok & 7)) << 4));
+  return tile + box * (kST * 128) + tok * 128 + ((chunk ^ (tok & 7)) << 4);
 }
 
 template <int HS>
@@ -105,6 +105,7 @@ slot_stream_fwd_kernel(const __grid_constant__ CUtensorMap tmTok, const SlotPara
   float4 acc[HS];
 #pragma unroll
   for (int i = 0; i < HS; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const uint32_t g_u = smem_u32(g_s), w_u = smem_u32(w_s);
   const float* Gs = p.G + b * HS;
   const float* c0s = p.c0 + b * HS;
 
@@ -115,7 +116,7 @@ slot_stream_fwd_kernel(const __grid_constant__ CUtensorMap tmTok, const SlotPara
     // keep the ring full: the stage being refilled was consumed in iteration it-1 (all threads passed its last barrier)
     if (tid == 0 && it + Cfg::STAGES - 1 < ntiles) issue(it + Cfg::STAGES - 1);
     mbar_wait(&full[st], (it / Cfg::STAGES) & 1);
-    const uint8_t* tile = smem + Cfg::OFF_TILE + st * kSTileBytes;
+    const uint32_t tile = smem_u32(smem + Cfg::OFF_TILE + st * kSTileBytes);
     const int tok_base = (tile0 + it) * kST;
 
     // ---------------- phase 1: partial dots over this lane's 48 channels of token tok_l
@@ -123,18 +124,18 @@ slot_stream_fwd_kernel(const __grid_constant__ CUtensorMap tmTok, const SlotPara
       float dot[HS];
 #pragma unroll
       for (int i = 0; i < HS; ++i) dot[i] = 0.f;
-      const float x0 = tile_chunk(tile, tok_l, 0)->x;   // shift for the one-pass moments (same for all slices of a token)
+      const float x0 = lds32(tile_chunk(tile, tok_l, 0));   // shift for the one-pass moments (same for all slices of a token)
       float s1 = 0.f, s2 = 0.f;
 #pragma unroll 4
       for (int c = 0; c < 12; ++c) {
         const int c4 = slice * 12 + c;
-        const float4 t = *tile_chunk(tile, tok_l, c4);
+        const float4 t = lds128(tile_chunk(tile, tok_l, c4));
         const float a0 = t.x - x0, a1 = t.y - x0, a2 = t.z - x0, a3 = t.w - x0;
         s1 += (a0 + a1) + (a2 + a3);
         s2 = fmaf(a0, a0, fmaf(a1, a1, fmaf(a2, a2, fmaf(a3, a3, s2))));
 #pragma unroll
         for (int i = 0; i < HS; ++i) {
-          const float4 gv = *reinterpret_cast<const float4*>(g_s + i * kSD + c4 * 4);
+          const float4 gv = lds128(g_u + (i * kSD + c4 * 4) * 4);
           dot[i] = fmaf(t.x, gv.x, fmaf(t.y, gv.y, fmaf(t.z, gv.z, fmaf(t.w, gv.w, dot[i]))));
         }
       }
@@ -166,7 +167,7 @@ slot_stream_fwd_kernel(const __grid_constant__ CUtensorMap tmTok, const SlotPara
         s1 += pp[HS];
         s2 += pp[HS + 1];
       }
-      const float x0 = tile_chunk(tile, lane, 0)->x;
+      const float x0 = lds32(tile_chunk(tile, lane, 0));
       const float d1 = s1 * (1.0f / kSD);
       const float mu = x0 + d1;
       const float var = fmaxf(s2 * (1.0f / kSD) - d1 * d1, 0.f);
@@ -205,10 +206,10 @@ slot_stream_fwd_kernel(const __grid_constant__ CUtensorMap tmTok, const SlotPara
     if (tid < kSD / 4) {
 #pragma unroll 4
       for (int j = 0; j < kST; ++j) {
-        const float4 t = *tile_chunk(tile, j, tid);
+        const float4 t = lds128(tile_chunk(tile, j, tid));
 #pragma unroll
         for (int i4 = 0; i4 < HS / 4; ++i4) {
-          const float4 w = *reinterpret_cast<const float4*>(w_s + j * HS + 4 * i4);
+          const float4 w = lds128(w_u + (j * HS + 4 * i4) * 4);
           float4& a0 = acc[4 * i4]; float4& a1 = acc[4 * i4 + 1]; float4& a2 = acc[4 * i4 + 2]; float4& a3 = acc[4 * i4 + 3];
           a0.x = fmaf(w.x, t.x, a0.x); a0.y = fmaf(w.x, t.y, a0.y); a0.z = fmaf(w.x, t.z, a0.z); a0.w = fmaf(w.x, t.w, a0.w);
           a1.x = fmaf(w.y, t.x, a1.x); a1.y = fmaf(w.y, t.y, a1.y); a1.z = fmaf(w.y, t.z, a1.z); a1.w = fmaf(w.y, t.w, a1.w);

@@ -144,6 +144,6 @@ def test_state_dict_roundtrip_and_weight_refresh():
         m2 = mk().cuda().eval(); m2.load_state_dict(sd2)
         c = m2(x)[1][0]
     assert not torch.allclose(a, b)
-    assert torch.equal(b, c)
+    assert torch.allclose(b, c, rtol=1e-4, atol=1e-5)   # identical weights -> identical logits (up to atomic summation order)
     with pytest.raises(RuntimeError):
         mk()(x.cpu())   # no CPU fallback
