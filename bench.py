@@ -46,6 +46,7 @@ def parse():
     ap.add_argument('--batch', type=int, default=0, help='clips per GPU (default: the workload recipe)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='eager launches instead of the captured CUDA graph')
     return ap.parse_args()
 
 
@@ -192,7 +193,7 @@ def main():
                                           num_scene_classes=365)
     model = model.to(dev).train()
     crit = TrainLoss(torch.nn.CrossEntropyLoss(), 'KL', C)
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0.05, fused=True)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0.05, fused=True, capturable=True)
     reducer = GradReducer(model) if world > 1 else None
 
     # synthetic step inputs: N(0,1) clips, random labels, FAME-like masks, teacher logits
@@ -219,27 +220,48 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------------------------------------------------------- warm-up
+    # ---------------------------------------------------------------- warm-up (+ graph capture of the whole step)
+    use_graph = not args.no_graph and world == 1
     for i in range(max(args.warmup, 3)):
         step(devb[i % nbuf])
     barrier()
+    graphed = None
+    if use_graph:
+        graphed = engine.GraphedTrainStep(model, crit, opt, devb, reducer=reducer, warmup=1)
+        for i in range(2):
+            graphed(i % nbuf)
+        barrier()
+
+    def run(i):
+        return graphed(i % nbuf) if graphed is not None else step(devb[i % nbuf])
 
     # ---------------------------------------------------------------- value: inputs resident in HBM
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    _lib.profile_begin()
     n0 = _lib.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
     for i in range(args.steps):
-        loss = step(devb[i % nbuf])
+        loss = run(i)
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
-    launches = _lib.launch_count() - n0
+    launches = (graphed.launches_per_step * args.steps) if graphed is not None else (_lib.launch_count() - n0)
+    # roofline leg: the same steps launched eagerly with every GEMM bracketed by CUDA events on its stream
+    # (events cannot be timed inside a replayed graph); same kernels, same shapes, same data
+    _lib.profile_begin()
+    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev2.record()
+    for i in range(args.steps):
+        step(devb[i % nbuf])
+    ev3.record()
+    barrier()
+    eager_ms = ev2.elapsed_time(ev3)
     gemm_ms, gemm_flops, gemm_n = _lib.profile_end(0)
+    attn_ms, attn_flops, attn_n = _lib.profile_end(1)
+    slot_ms, slot_bytes, slot_n = _lib.profile_end(2)
     clk = clocks.stop() if rank == 0 else None
     loss_val = float(loss)
     assert loss_val == loss_val, 'loss is NaN'
@@ -271,7 +293,7 @@ def main():
             if i + 1 < args.steps:
                 h2d(i + 1)
             main_stream.wait_event(ready[i % nbuf])
-            l = step(devb[i % nbuf])
+            l = run(i)
             done[i % nbuf].record(main_stream)
             loss_host[i:i + 1].copy_(l.reshape(1), non_blocking=True)
         e1.record()
@@ -304,12 +326,15 @@ def main():
                                    f'(fwd + TrainLoss + bwd + fused AdamW), drop_path {cfg["drop_path_rate"]}',
                        'clips_per_gpu': B, 'global_batch': B * world, 'parallelism': f'dp{world}',
                        'l2': 'per-step working set (activations + weights, several GB) far exceeds the 126 MB L2; no flush needed',
-                       'loss': loss_val},
+                       'loss': loss_val, 'launch_mode': 'cuda-graph replay of the whole step' if graphed is not None else 'eager'},
             'clocks': clk,
             'gpu_launches': int(launches),
             'roofline': {'kernel': 'gemm_bf16_kernel (tcgen05/TMEM/TMA)', 'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf,
                          'unit': 'TFLOP/s', 'frac': achieved / peak_tf, 'traffic': traffic, 'peak_source': f'{peak_src} (sustained cuBLAS bf16)',
-                         'launches': int(gemm_n), 'share_of_step': gemm_ms / ms,
+                         'launches': int(gemm_n), 'share_of_step': gemm_ms / eager_ms, 'timed_over': 'eager re-run of the timed steps',
+                         'eager_ms_per_step': eager_ms / args.steps,
+                         'attention': {'tflops': attn_flops / (attn_ms * 1e-3) / 1e12 if attn_ms > 0 else None, 'share_of_step': attn_ms / eager_ms, 'launches': int(attn_n)},
+                         'slot_attention': {'gbs': slot_bytes / (slot_ms * 1e-3) / 1e9 if slot_ms > 0 else None, 'peak_gbs': peak_gbs, 'share_of_step': slot_ms / eager_ms, 'launches': int(slot_n)},
                          'step_tensor_frac': value / world * TRAIN_GFLOP_PER_CLIP / 1e3 / peak_tf},
         }
         if e2e_ms:

@@ -222,7 +222,7 @@ extern "C" int devias_colsum_bf16(const void* a, int64_t lda, int rows, int cols
   DV_REQUIRE(a && out, "null pointer");
   DV_REQUIRE(cols % 8 == 0 && lda % 8 == 0, "cols and lda must be multiples of 8");
   if (rows <= 0) return DEVIAS_OK;
-  const int rows_per_block = 512;
+  const int rows_per_block = 128;   // 768 x 12544 -> 294 blocks (>= 1 per SM), 16 rows in flight per thread
   dim3 grid((cols + 255) / 256, (rows + rows_per_block - 1) / rows_per_block);
   colsum_bf16_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(a), lda, rows, cols,
                                                                          out, rows_per_block);

@@ -47,3 +47,60 @@ def validation_step(model, videos, target):
     acc1 = (top5[:, 0] == target).float().mean() * 100.0
     acc5 = (top5 == target.unsqueeze(1)).any(dim=1).float().mean() * 100.0
     return output, scene_output, loss, acc1, acc5
+
+
+class GraphedTrainStep:
+    """The whole training step (student forward, TrainLoss, backward, gradient exchange, optimizer update) captured once
+    into a CUDA graph and replayed: the ~2000 kernel launches of a step cost one graph launch, which removes the host
+    launch overhead that otherwise bounds small-batch steps ('launch-bound').
+
+    `batches`: one or more dicts of STATIC device tensors {clip, target, fg, fgf, teacher}; one graph is captured per
+    dict (they share a memory pool), so input buffers can be double-buffered against host->device copies.
+    The optimizer must be capture-safe (e.g. torch.optim.AdamW(fused=True, capturable=True)).
+    """
+
+    def __init__(self, model, train_criterion, optimizer, batches, reducer=None, warmup=3):
+        self.model, self.crit, self.opt, self.reducer = model, train_criterion, optimizer, reducer
+        self.batches = list(batches)
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):                      # warm-up off the capture stream (allocator, lazy inits)
+            for i in range(warmup):
+                self._body(self.batches[i % len(self.batches)])
+                self._zero()
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        self.graphs, self.losses = [], []
+        pool = None
+        from . import _lib
+        for b in self.batches:
+            g = torch.cuda.CUDAGraph()
+            n0 = _lib.launch_count()
+            with torch.cuda.graph(g, pool=pool):
+                loss = self._body(b)
+            self.launches_per_step = _lib.launch_count() - n0
+            pool = g.pool()
+            self.graphs.append(g)
+            self.losses.append(loss)
+            self._zero()
+
+    def _zero(self):
+        if self.reducer is not None:
+            self.reducer.zero_grad()
+        else:
+            self.opt.zero_grad(set_to_none=True)
+
+    def _body(self, b):
+        loss, _, _ = train_class_batch(self.model, None, b['clip'], b['target'], self.crit, (b['fg'], b['fgf']),
+                                       teacher_logits=b['teacher'])
+        loss.backward()
+        if self.reducer is not None:
+            self.reducer.finish()
+        self.opt.step()
+        return loss.detach()
+
+    def __call__(self, index=0):
+        """replay the step on static batch `index`; returns the (static) loss tensor of that graph"""
+        self.graphs[index].replay()
+        return self.losses[index]

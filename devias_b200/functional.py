@@ -47,13 +47,11 @@ def _flat_zeros(like_list, device):
 
 
 def _wgrad_split(rows_out: int, cols_out: int, tokens: int) -> int:
-    """split-K factor so that a weight-gradient GEMM (K = tokens) fills the 148 SMs."""
-    tiles = ((rows_out + 127) // 128) * ((cols_out + 255) // 256)
-    if cols_out % 256 != 0:
-        tiles = ((rows_out + 127) // 128) * ((cols_out + 127) // 128)
+    """split-K factor so that a weight-gradient GEMM (K = tokens) fills the 74 two-CTA clusters about twice."""
+    bn = 256 if cols_out % 256 == 0 else 128
+    pair_tiles = (((rows_out + 127) // 128 + 1) // 2) * ((cols_out + bn - 1) // bn)
     kblks = (tokens + 63) // 64
-    s = max(1, min(kblks, (2 * 148 + tiles - 1) // tiles))
-    return s
+    return max(1, min(kblks, (2 * 74 + pair_tiles - 1) // pair_tiles))
 
 
 # --------------------------------------------------------------------------------------------
