@@ -1,12 +1,17 @@
 // Persistent warp-specialised bf16 GEMM for sm_100a: TMA -> 128B-swizzled smem ring -> tcgen05.mma (cta_group::1,
-// 128 x BN x 16) -> fp32 accumulators double-buffered in tensor memory -> fused epilogue straight from TMEM.
+// 128 x BN x 16) -> fp32 accumulators double-buffered in tensor memory -> fused epilogue -> TMA store / TMA reduce-add.
 // CTAs run as clusters of two along M: the pair shares its B (weight) tile -- each CTA fetches half of it and TMA-multicasts
-// it into both shared memories -- which cuts L2->SM operand traffic per FLOP by a third (ncu: the 1-CTA version was
-// L2-bandwidth bound at ~45% tensor-pipe utilisation).
+// it into both shared memories.
 //
 //   warp 0      : TMA producer (one elected lane)
 //   warp 1      : TMEM allocator + MMA issuer (one elected lane)
-//   warps 2..5  : epilogue (TMEM lane quarter = warp_idx % 4), overlapped with the next tile's MMAs
+//   warps 2..9  : epilogue (TMEM lane quarter = warp_idx % 4; the two warps of a quarter split the tile's columns),
+//                 overlapped with the next tile's MMAs.  Each warp owns a 32-row x 128-byte staging box: it reads its
+//                 accumulator rows from TMEM (thread = row), applies the epilogue, writes the box 128B-swizzled and one lane
+//                 issues a bulk tensor store (or reduce-add for split-K weight gradients); residual / pre-activation
+//                 operands arrive the same way (bulk tensor load into a second box, one box ahead).  Global memory is thus
+//                 only touched by TMA in full lines -- the first version's row-per-thread LDG/STG epilogue was L1-tag bound
+//                 (32 sectors per instruction; ncu l1tex ~50 %, K=768 GEMMs at 370-850 TFLOP/s).
 //
 // Replaces the cuBLAS calls behind F.linear in model/modeling_slot.py:101,113,61,65 (and their autograd
 // dgrad / wgrad) -- see include/devias_b200.h for the epilogue catalogue.
@@ -18,107 +23,68 @@ namespace dv {
 struct GemmParams {
   int M, N, K;
   int splits;
-  void* out; long long ldo;
-  void* out2; long long ldo2;
   const float* bias;
-  const void* aux; long long ldaux; int aux_row_mod;
+  int aux_row_mod;
   const float* row_scale; int rows_per_scale;
 };
 
 constexpr int kBM = 128;
 constexpr int kBK = 64;
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;   // TMA warp + MMA warp + 8 epilogue warps
+constexpr int kBoxBytes = 32 * 128; // one epilogue staging box: 32 rows x 128 B
 
-template <int BN>
+template <int EPI>
+struct EpiTraits {
+  static constexpr bool OUT_F32 = EPI == DEVIAS_EPI_STORE_F32 || EPI == DEVIAS_EPI_RESID_F32 || EPI == DEVIAS_EPI_ATOMIC_F32;
+  static constexpr bool HAS_AUX = EPI == DEVIAS_EPI_RESID_F32 || EPI == DEVIAS_EPI_DGELU_BF16;
+  static constexpr bool TWO_OUT = EPI == DEVIAS_EPI_GELU_BF16;
+  static constexpr int BOX_COLS = OUT_F32 ? 32 : 64;   // 128 bytes of output per row
+  static constexpr int BOXES_PER_WARP_SMEM = (HAS_AUX || TWO_OUT) ? 2 : 1;
+};
+
+template <int BN, int EPI>
 struct GemmCfg {
   static constexpr int A_BYTES = kBM * kBK * 2;
   static constexpr int B_BYTES = BN * kBK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : 6;
-  static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual 1 KiB alignment
+  static constexpr int EPI_BYTES = 8 * EpiTraits<EPI>::BOXES_PER_WARP_SMEM * kBoxBytes;   // 32 or 64 KiB
+  static constexpr int FIT = (227 * 1024 - 2048 - EPI_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = FIT > 6 ? 6 : FIT;
+  static constexpr int OFF_EPI = STAGES * STAGE_BYTES;
+  static constexpr int OFF_BAR = OFF_EPI + EPI_BYTES;
+  static constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;  // +1024: manual 1 KiB alignment
   static constexpr uint32_t TMEM_COLS = 2 * BN;
 };
 
-template <int EPI>
-__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int row, int col0, const uint32_t (&acc)[32]) {
-  // one thread: row `row`, 32 consecutive columns starting at col0
-  float v[32];
+// one staging row (128 B) <-> registers, 128B-swizzled: 16-byte chunk c of row r lives at chunk c ^ (r & 7)
+__device__ __forceinline__ void stage_write_row(uint32_t box, int r, const uint32_t (&v)[32]) {
 #pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
-  if constexpr (EPI != DEVIAS_EPI_DGELU_BF16 && EPI != DEVIAS_EPI_ATOMIC_F32) {
-    if (p.bias != nullptr) {
-      const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+  for (int c = 0; c < 8; ++c) sts128(box + r * 128 + ((c ^ (r & 7)) << 4), v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+}
+__device__ __forceinline__ void stage_read_row(uint32_t box, int r, uint32_t (&v)[32]) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float4 b = __ldg(b4 + i);
-        v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
-      }
-    }
-  }
-  if constexpr (EPI == DEVIAS_EPI_STORE_BF16) {
-    uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ldo + col0);
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-      o[i] = make_uint4(pack_bf16(v[8 * i], v[8 * i + 1]), pack_bf16(v[8 * i + 2], v[8 * i + 3]),
-                        pack_bf16(v[8 * i + 4], v[8 * i + 5]), pack_bf16(v[8 * i + 6], v[8 * i + 7]));
-  } else if constexpr (EPI == DEVIAS_EPI_STORE_F32) {
-    float4* o = reinterpret_cast<float4*>(static_cast<float*>(p.out) + (long long)row * p.ldo + col0);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-  } else if constexpr (EPI == DEVIAS_EPI_GELU_BF16) {
-    uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ldo + col0);
-    uint4* o2 = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out2) + (long long)row * p.ldo2 + col0);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      o[i] = make_uint4(pack_bf16(v[8 * i], v[8 * i + 1]), pack_bf16(v[8 * i + 2], v[8 * i + 3]),
-                        pack_bf16(v[8 * i + 4], v[8 * i + 5]), pack_bf16(v[8 * i + 6], v[8 * i + 7]));
-      float g[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) g[j] = gelu_fast(v[8 * i + j]);
-      o2[i] = make_uint4(pack_bf16(g[0], g[1]), pack_bf16(g[2], g[3]), pack_bf16(g[4], g[5]), pack_bf16(g[6], g[7]));
-    }
-  } else if constexpr (EPI == DEVIAS_EPI_DGELU_BF16) {
-    const uint4* a = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.aux) + (long long)row * p.ldaux + col0);
-    uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ldo + col0);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const uint4 h = __ldg(a + i);
-      const float2 h0 = unpack_bf16(h.x), h1 = unpack_bf16(h.y), h2 = unpack_bf16(h.z), h3 = unpack_bf16(h.w);
-      o[i] = make_uint4(pack_bf16(v[8 * i] * gelu_fast_grad(h0.x), v[8 * i + 1] * gelu_fast_grad(h0.y)),
-                        pack_bf16(v[8 * i + 2] * gelu_fast_grad(h1.x), v[8 * i + 3] * gelu_fast_grad(h1.y)),
-                        pack_bf16(v[8 * i + 4] * gelu_fast_grad(h2.x), v[8 * i + 5] * gelu_fast_grad(h2.y)),
-                        pack_bf16(v[8 * i + 6] * gelu_fast_grad(h3.x), v[8 * i + 7] * gelu_fast_grad(h3.y)));
-    }
-  } else if constexpr (EPI == DEVIAS_EPI_RESID_F32) {
-    const int arow = p.aux_row_mod > 0 ? row % p.aux_row_mod : row;
-    const float s = p.row_scale != nullptr ? __ldg(p.row_scale + row / p.rows_per_scale) : 1.0f;
-    const float4* a = reinterpret_cast<const float4*>(static_cast<const float*>(p.aux) + (long long)arow * p.ldaux + col0);
-    float4* o = reinterpret_cast<float4*>(static_cast<float*>(p.out) + (long long)row * p.ldo + col0);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float4 r = __ldg(a + i);
-      o[i] = make_float4(fmaf(s, v[4 * i], r.x), fmaf(s, v[4 * i + 1], r.y), fmaf(s, v[4 * i + 2], r.z),
-                         fmaf(s, v[4 * i + 3], r.w));
-    }
-  } else if constexpr (EPI == DEVIAS_EPI_ATOMIC_F32) {
-    float* o = static_cast<float*>(p.out) + (long long)row * p.ldo + col0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) red_add_v4_f32(o + 4 * i, v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  for (int c = 0; c < 8; ++c) {
+    const float4 t = lds128(box + r * 128 + ((c ^ (r & 7)) << 4));
+    v[4 * c] = __float_as_uint(t.x); v[4 * c + 1] = __float_as_uint(t.y);
+    v[4 * c + 2] = __float_as_uint(t.z); v[4 * c + 3] = __float_as_uint(t.w);
   }
 }
 
 template <int BN, bool A_MN, bool B_MN, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
-gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2,
+                 const __grid_constant__ CUtensorMap tmAux, const GemmParams p) {
+  using Cfg = GemmCfg<BN, EPI>;
+  using ET = EpiTraits<EPI>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
   uint64_t* empty_bar = full_bar + Cfg::STAGES;
   uint64_t* tfull_bar = empty_bar + Cfg::STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* aux_bar = tempty_bar + 2;                 // one per epilogue warp
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + 8);
 
   const int warp = threadIdx.x >> 5;
   const int rank = (int)cluster_ctarank();          // 0/1: which half of the 256-row pair tile / which half of B we fetch
@@ -133,6 +99,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0 && elect_one()) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
+    prefetch_tmap(&tmOut);
+    if constexpr (ET::TWO_OUT) prefetch_tmap(&tmOut2);
+    if constexpr (ET::HAS_AUX) prefetch_tmap(&tmAux);
   }
   if (warp == 1) {
     if (elect_one()) {
@@ -142,8 +111,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       for (int s = 0; s < 2; ++s) {
         mbar_init(&tfull_bar[s], 1);
-        mbar_init(&tempty_bar[s], 4);
+        mbar_init(&tempty_bar[s], 8);
       }
+      for (int s = 0; s < 8; ++s) mbar_init(&aux_bar[s], 1);
       fence_barrier_init();
     }
     __syncwarp();
@@ -231,8 +201,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     __syncwarp();
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ------------------------------------------------------------------ epilogue (warps 2..9)
+    const int ew = warp - 2;              // 0..7
+    const int q = warp & 3;               // TMEM lane quarter this warp may access
+    const int chalf = ew >> 2;            // which half of the tile's columns this warp drains
+    const int lane = (int)lane_id();
+    constexpr int kBoxes = (BN / 2) / ET::BOX_COLS;          // output boxes per warp per tile
+    uint8_t* box_out_p = smem + Cfg::OFF_EPI + ew * ET::BOXES_PER_WARP_SMEM * kBoxBytes;
+    uint8_t* box_aux_p = box_out_p + kBoxBytes;              // second box: aux operand (RESID/DGELU) or second output (GELU)
+    const uint32_t box_out = smem_u32(box_out_p);
+    const uint32_t box_aux = box_out + kBoxBytes;
+    uint64_t* my_aux_bar = &aux_bar[ew];
+    uint32_t aux_uses = 0;
     int it = 0;
     for (int t = cluster_id; t < tiles; t += n_clusters, ++it) {
       const int split = t / (m_pairs * n_blks);
@@ -240,22 +220,113 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int m_blk = 2 * (rem / n_blks) + rank, n_blk = rem % n_blks;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
+      const int row0 = m_blk * kBM + q * 32;                 // first of this warp's 32 rows
+      const int row = row0 + lane;
+      const int colbase = n_blk * BN + chalf * (BN / 2);
+      const bool active = row0 < p.M && colbase < p.N;       // warp-uniform
+      float rs = 1.0f;
+      if constexpr (EPI == DEVIAS_EPI_RESID_F32) {
+        if (active && p.row_scale != nullptr && row < p.M) rs = __ldg(p.row_scale + row / p.rows_per_scale);
+      }
+      auto issue_aux = [&](int b) {   // lane 0: bulk tensor load of aux box b (rows of `aux` may repeat modulo aux_row_mod)
+        const int arow0 = p.aux_row_mod > 0 ? row0 % p.aux_row_mod : row0;
+        mbar_arrive_expect_tx(my_aux_bar, kBoxBytes);
+        tma_load_2d(box_aux_p, &tmAux, my_aux_bar, colbase + b * ET::BOX_COLS, arow0);
+      };
+      if constexpr (ET::HAS_AUX) {
+        if (active && lane == 0) issue_aux(0);
+      }
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
-      const int row = m_blk * kBM + q * 32 + (int)lane_id();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + chalf * (BN / 2);
+      if (active) {
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t acc[32];
-        tmem_ld_32x32b_x32(taddr + c * 32, acc);
-        tmem_ld_wait();
-        const int col0 = n_blk * BN + c * 32;
-        if (row < p.M && col0 < p.N) epilogue_chunk<EPI>(p, row, col0, acc);
+        for (int b = 0; b < kBoxes; ++b) {
+          const int col0 = colbase + b * ET::BOX_COLS;
+          if (col0 >= p.N) break;                            // warp-uniform (ragged N)
+          // ---- auxiliary operand of this box -> registers; then prefetch the next one
+          uint32_t aux[ET::HAS_AUX ? 32 : 1];
+          if constexpr (ET::HAS_AUX) {
+            mbar_wait(my_aux_bar, aux_uses & 1);
+            ++aux_uses;
+            stage_read_row(box_aux, lane, aux);
+            __syncwarp();
+            if (lane == 0 && b + 1 < kBoxes && col0 + ET::BOX_COLS < p.N) issue_aux(b + 1);
+          }
+          // ---- accumulator -> registers, epilogue math, packed into `outv` (32 x 32-bit = one 128-byte row)
+          uint32_t outv[32];
+          uint32_t outv2[ET::TWO_OUT ? 32 : 1];
+          if constexpr (ET::OUT_F32) {
+            uint32_t acc[32];
+            tmem_ld_32x32b_x32(taddr + b * 32, acc);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float4 v = make_float4(__uint_as_float(acc[4 * i]), __uint_as_float(acc[4 * i + 1]), __uint_as_float(acc[4 * i + 2]),
+                                     __uint_as_float(acc[4 * i + 3]));
+              if constexpr (EPI != DEVIAS_EPI_ATOMIC_F32) {
+                if (p.bias != nullptr) {
+                  const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + i);
+                  v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+                }
+              }
+              if constexpr (EPI == DEVIAS_EPI_RESID_F32) {
+                v.x = fmaf(rs, v.x, __uint_as_float(aux[4 * i])); v.y = fmaf(rs, v.y, __uint_as_float(aux[4 * i + 1]));
+                v.z = fmaf(rs, v.z, __uint_as_float(aux[4 * i + 2])); v.w = fmaf(rs, v.w, __uint_as_float(aux[4 * i + 3]));
+              }
+              outv[4 * i] = __float_as_uint(v.x); outv[4 * i + 1] = __float_as_uint(v.y);
+              outv[4 * i + 2] = __float_as_uint(v.z); outv[4 * i + 3] = __float_as_uint(v.w);
+            }
+          } else {
+#pragma unroll
+            for (int hlf = 0; hlf < 2; ++hlf) {              // 64 output columns = two 32-column TMEM reads
+              uint32_t acc[32];
+              tmem_ld_32x32b_x32(taddr + b * 64 + hlf * 32, acc);
+              tmem_ld_wait();
+              const int cc = col0 + hlf * 32;
+              const bool has_bias = EPI != DEVIAS_EPI_DGELU_BF16 && p.bias != nullptr && cc < p.N;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                float4 v = make_float4(__uint_as_float(acc[4 * i]), __uint_as_float(acc[4 * i + 1]), __uint_as_float(acc[4 * i + 2]),
+                                       __uint_as_float(acc[4 * i + 3]));
+                if (has_bias) {
+                  const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + cc) + i);
+                  v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+                }
+                if constexpr (EPI == DEVIAS_EPI_DGELU_BF16) {
+                  const float2 h0 = unpack_bf16(aux[hlf * 16 + 2 * i]), h1 = unpack_bf16(aux[hlf * 16 + 2 * i + 1]);
+                  v.x *= gelu_fast_grad(h0.x); v.y *= gelu_fast_grad(h0.y); v.z *= gelu_fast_grad(h1.x); v.w *= gelu_fast_grad(h1.y);
+                }
+                outv[hlf * 16 + 2 * i] = pack_bf16(v.x, v.y);
+                outv[hlf * 16 + 2 * i + 1] = pack_bf16(v.z, v.w);
+                if constexpr (ET::TWO_OUT) {
+                  outv2[hlf * 16 + 2 * i] = pack_bf16(gelu_fast(v.x), gelu_fast(v.y));
+                  outv2[hlf * 16 + 2 * i + 1] = pack_bf16(gelu_fast(v.z), gelu_fast(v.w));
+                }
+              }
+            }
+          }
+          // ---- staging box free again? (the previous bulk store of this warp has finished READING it)
+          if (lane == 0) bulk_wait_read0();
+          __syncwarp();
+          stage_write_row(box_out, lane, outv);
+          if constexpr (ET::TWO_OUT) stage_write_row(box_aux, lane, outv2);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (EPI == DEVIAS_EPI_ATOMIC_F32) tma_reduce_add_2d(&tmOut, box_out_p, col0, row0);
+            else tma_store_2d(&tmOut, box_out_p, col0, row0);
+            if constexpr (ET::TWO_OUT) tma_store_2d(&tmOut2, box_aux_p, col0, row0);
+            bulk_commit();
+          }
+        }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane_id() == 0) mbar_arrive(&tempty_bar[as]);
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
     }
+    if (lane == 0) bulk_wait0();   // all of this warp's stores / reductions are complete before the CTA may exit
+    __syncwarp();
   }
   tc_fence_before();
   __syncthreads();
@@ -267,17 +338,48 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------------ host
+struct GemmHostArgs {
+  const void* a; long long lda; const void* b; long long ldb;
+  void* out; long long ldo; void* out2; long long ldo2;
+  const void* aux; long long ldaux;
+};
+
+static int make_tmap_2d(CUtensorMap* out, CUtensorMapDataType dt, int elem_bytes, const void* base, uint64_t inner, uint64_t outer,
+                        uint64_t row_stride_elems, uint32_t box_inner, uint32_t box_outer) {
+  const uint64_t dims[2] = {inner, outer};
+  const uint64_t str[1] = {row_stride_elems * elem_bytes};
+  const uint32_t box[2] = {box_inner, box_outer};
+  return make_tmap_nd(out, dt, 2, base, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
 template <int BN, bool A_MN, bool B_MN, int EPI>
-static int launch_gemm(const void* a, long long lda, const void* b, long long ldb, const GemmParams& p, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
-  CUtensorMap tmA, tmB;
+static int launch_gemm(const GemmHostArgs& h, const GemmParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN, EPI>;
+  using ET = EpiTraits<EPI>;
+  static_assert(Cfg::STAGES >= 3, "pipeline too shallow");
+  CUtensorMap tmA, tmB, tmOut, tmOut2, tmAux;
   int rc;
-  if (!A_MN) rc = make_tmap_2d_bf16(&tmA, a, p.K, p.M, lda * 2, kBK, kBM);
-  else rc = make_tmap_2d_bf16(&tmA, a, p.M, p.K, lda * 2, 64, kBK);
+  if (!A_MN) rc = make_tmap_2d_bf16(&tmA, h.a, p.K, p.M, h.lda * 2, kBK, kBM);
+  else rc = make_tmap_2d_bf16(&tmA, h.a, p.M, p.K, h.lda * 2, 64, kBK);
   if (rc) return rc;
-  if (!B_MN) rc = make_tmap_2d_bf16(&tmB, b, p.K, p.N, ldb * 2, kBK, BN / 2);   // each CTA of a pair fetches half of B
-  else rc = make_tmap_2d_bf16(&tmB, b, p.N, p.K, ldb * 2, 64, kBK);
+  if (!B_MN) rc = make_tmap_2d_bf16(&tmB, h.b, p.K, p.N, h.ldb * 2, kBK, BN / 2);   // each CTA of a pair fetches half of B
+  else rc = make_tmap_2d_bf16(&tmB, h.b, p.N, p.K, h.ldb * 2, 64, kBK);
   if (rc) return rc;
+  const CUtensorMapDataType odt = ET::OUT_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const int obytes = ET::OUT_F32 ? 4 : 2;
+  rc = make_tmap_2d(&tmOut, odt, obytes, h.out, p.N, p.M, h.ldo, ET::BOX_COLS, 32);
+  if (rc) return rc;
+  tmOut2 = tmOut;
+  tmAux = tmOut;
+  if (ET::TWO_OUT) {
+    rc = make_tmap_2d(&tmOut2, odt, obytes, h.out2, p.N, p.M, h.ldo2, ET::BOX_COLS, 32);
+    if (rc) return rc;
+  }
+  if (ET::HAS_AUX) {
+    const uint64_t arows = p.aux_row_mod > 0 ? (uint64_t)p.aux_row_mod : (uint64_t)p.M;
+    rc = make_tmap_2d(&tmAux, odt, obytes, h.aux, p.N, arows, h.ldaux, ET::BOX_COLS, 32);
+    if (rc) return rc;
+  }
   auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, EPI>;
   static bool attr_done = false;
   if (!attr_done) {
@@ -289,7 +391,7 @@ static int launch_gemm(const void* a, long long lda, const void* b, long long ld
   const int max_clusters = sm_count() / 2;
   const int grid = 2 * (pair_tiles < max_clusters ? pair_tiles : max_clusters);
   const int prof = prof_begin(DEVIAS_PROF_GEMM, 2.0 * p.M * (double)p.N * p.K, stream);
-  kern<<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  kern<<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmOut, tmOut2, tmAux, p);
   prof_end(prof, stream);
   DV_CHECK_CUDA(cudaGetLastError());
   count_launch();
@@ -297,20 +399,18 @@ static int launch_gemm(const void* a, long long lda, const void* b, long long ld
 }
 
 template <int BN, int EPI>
-static int dispatch_layout(bool a_mn, bool b_mn, const void* a, long long lda, const void* b, long long ldb,
-                           const GemmParams& p, cudaStream_t s) {
-  if (!a_mn && !b_mn) return launch_gemm<BN, false, false, EPI>(a, lda, b, ldb, p, s);
-  if (!a_mn && b_mn) return launch_gemm<BN, false, true, EPI>(a, lda, b, ldb, p, s);
-  if (a_mn && b_mn) return launch_gemm<BN, true, true, EPI>(a, lda, b, ldb, p, s);
+static int dispatch_layout(bool a_mn, bool b_mn, const GemmHostArgs& h, const GemmParams& p, cudaStream_t s) {
+  if (!a_mn && !b_mn) return launch_gemm<BN, false, false, EPI>(h, p, s);
+  if (!a_mn && b_mn) return launch_gemm<BN, false, true, EPI>(h, p, s);
+  if (a_mn && b_mn) return launch_gemm<BN, true, true, EPI>(h, p, s);
   set_last_error("layout", "A mn-major with B k-major is not instantiated (no caller on the DEVIAS path)", __FILE__, __LINE__);
   return DEVIAS_ERR_UNSUPPORTED;
 }
 
 template <int EPI>
-static int dispatch_bn(int bn, bool a_mn, bool b_mn, const void* a, long long lda, const void* b, long long ldb,
-                       const GemmParams& p, cudaStream_t s) {
-  if (bn == 256) return dispatch_layout<256, EPI>(a_mn, b_mn, a, lda, b, ldb, p, s);
-  return dispatch_layout<128, EPI>(a_mn, b_mn, a, lda, b, ldb, p, s);
+static int dispatch_bn(int bn, bool a_mn, bool b_mn, const GemmHostArgs& h, const GemmParams& p, cudaStream_t s) {
+  if (bn == 256) return dispatch_layout<256, EPI>(a_mn, b_mn, h, p, s);
+  return dispatch_layout<128, EPI>(a_mn, b_mn, h, p, s);
 }
 
 }  // namespace dv
@@ -328,9 +428,14 @@ extern "C" int devias_gemm_bf16(const void* a, int64_t lda, int a_mn_major, cons
                  (reinterpret_cast<uintptr_t>(out) & 15) == 0,
              "operands must be 16-byte aligned");
   DV_REQUIRE(ldo % 8 == 0, "ldo must be a multiple of 8");
-  if (epilogue == DEVIAS_EPI_GELU_BF16) DV_REQUIRE(out2 && ldo2 % 8 == 0, "GELU epilogue needs out2");
-  if (epilogue == DEVIAS_EPI_DGELU_BF16) DV_REQUIRE(aux && ldaux % 8 == 0, "DGELU epilogue needs aux");
-  if (epilogue == DEVIAS_EPI_RESID_F32) DV_REQUIRE(aux && ldaux % 4 == 0, "RESID epilogue needs aux");
+  if (epilogue == DEVIAS_EPI_GELU_BF16)
+    DV_REQUIRE(out2 && ldo2 % 8 == 0 && (reinterpret_cast<uintptr_t>(out2) & 15) == 0, "GELU epilogue needs out2");
+  if (epilogue == DEVIAS_EPI_DGELU_BF16)
+    DV_REQUIRE(aux && ldaux % 8 == 0 && (reinterpret_cast<uintptr_t>(aux) & 15) == 0, "DGELU epilogue needs aux");
+  if (epilogue == DEVIAS_EPI_RESID_F32) {
+    DV_REQUIRE(aux && ldaux % 4 == 0 && (reinterpret_cast<uintptr_t>(aux) & 15) == 0, "RESID epilogue needs aux");
+    DV_REQUIRE(aux_row_mod == 0 || aux_row_mod % 32 == 0, "aux_row_mod must be a multiple of 32 (epilogue boxes are 32 rows)");
+  }
   if (row_scale) DV_REQUIRE(rows_per_scale > 0, "rows_per_scale");
   const int k_blks = (k + kBK - 1) / kBK;
   int splits = split_k < 1 ? 1 : split_k;
@@ -340,22 +445,21 @@ extern "C" int devias_gemm_bf16(const void* a, int64_t lda, int a_mn_major, cons
     const int per = (k_blks + splits - 1) / splits;
     splits = (k_blks + per - 1) / per;
   }
-  GemmParams p{m, n, k, splits, out, (long long)ldo, out2, (long long)ldo2, bias, aux, (long long)ldaux, aux_row_mod,
-               row_scale, rows_per_scale};
-  // BN = 256 maximises operand reuse; fall back to 128 when that leaves too few tiles for 148 SMs
+  GemmParams p{m, n, k, splits, bias, aux_row_mod, row_scale, rows_per_scale};
+  GemmHostArgs h{a, (long long)lda, b, (long long)ldb, out, (long long)ldo, out2, (long long)ldo2, aux, (long long)ldaux};
+  // BN = 256 maximises operand reuse; fall back to 128 when that leaves too few tiles for the 74 clusters
   const int m_blks = (m + kBM - 1) / kBM;
   int bn = 256;
   if (n % 256 != 0 || ((m_blks + 1) / 2) * (n / 256) * splits < sm_count() / 2) bn = 128;
-  if (n % 128 != 0 && bn == 128) bn = 128;  // tail columns are masked per 32-col chunk
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const bool amn = a_mn_major != 0, bmn = b_mn_major != 0;
   switch (epilogue) {
-    case DEVIAS_EPI_STORE_BF16: return dispatch_bn<DEVIAS_EPI_STORE_BF16>(bn, amn, bmn, a, lda, b, ldb, p, s);
-    case DEVIAS_EPI_STORE_F32: return dispatch_bn<DEVIAS_EPI_STORE_F32>(bn, amn, bmn, a, lda, b, ldb, p, s);
-    case DEVIAS_EPI_GELU_BF16: return dispatch_bn<DEVIAS_EPI_GELU_BF16>(bn, amn, bmn, a, lda, b, ldb, p, s);
-    case DEVIAS_EPI_DGELU_BF16: return dispatch_bn<DEVIAS_EPI_DGELU_BF16>(bn, amn, bmn, a, lda, b, ldb, p, s);
-    case DEVIAS_EPI_RESID_F32: return dispatch_bn<DEVIAS_EPI_RESID_F32>(bn, amn, bmn, a, lda, b, ldb, p, s);
-    case DEVIAS_EPI_ATOMIC_F32: return dispatch_bn<DEVIAS_EPI_ATOMIC_F32>(bn, amn, bmn, a, lda, b, ldb, p, s);
+    case DEVIAS_EPI_STORE_BF16: return dispatch_bn<DEVIAS_EPI_STORE_BF16>(bn, amn, bmn, h, p, s);
+    case DEVIAS_EPI_STORE_F32: return dispatch_bn<DEVIAS_EPI_STORE_F32>(bn, amn, bmn, h, p, s);
+    case DEVIAS_EPI_GELU_BF16: return dispatch_bn<DEVIAS_EPI_GELU_BF16>(bn, amn, bmn, h, p, s);
+    case DEVIAS_EPI_DGELU_BF16: return dispatch_bn<DEVIAS_EPI_DGELU_BF16>(bn, amn, bmn, h, p, s);
+    case DEVIAS_EPI_RESID_F32: return dispatch_bn<DEVIAS_EPI_RESID_F32>(bn, amn, bmn, h, p, s);
+    case DEVIAS_EPI_ATOMIC_F32: return dispatch_bn<DEVIAS_EPI_ATOMIC_F32>(bn, amn, bmn, h, p, s);
     default: break;
   }
   set_last_error("epilogue", "unknown epilogue id", __FILE__, __LINE__);
