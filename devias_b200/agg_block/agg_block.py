@@ -89,10 +89,11 @@ class AggregationBlock(nn.Module):
         with torch.autocast('cuda', enabled=False):
             x = self.get_queries(data.shape[0]).float()
             mu, r = slot_kernels.token_stats(data)
+            sink = slot_kernels.new_sink() if (torch.is_grad_enabled() and data.requires_grad) else None
             sim = None
             for cross_attn, _, cross_ff, _ in self.layers:
                 attn, sim = SA.slot_attention_layer(x, data, mu, r, self._layer_params(cross_attn),
-                                                    stream=slot_kernels.slot_stream)
+                                                    stream=slot_kernels.slot_stream, sink=sink)
                 x = attn + x
                 x = cross_ff(x) + x
             return self.last_layer(x), sim

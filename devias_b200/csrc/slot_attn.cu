@@ -235,6 +235,263 @@ slot_stream_fwd_kernel(const __grid_constant__ CUtensorMap tmTok, const SlotPara
   }
 }
 
+// =====================================================================================================================
+// Backward of the streaming step.  Saved from the forward: the slot-softmax a[sh, j] and the token statistics (mu, r).
+//   f[sh]    = dU[sh] . t_j + dm[sh] mu_j                      e[sh] = g[sh] . t_j - mu_j G[sh]
+//   da[sh]   = r_j f[sh] + dA[sh] + dattn[sh, j]
+//   dsim[sh] = a[sh] (da[sh] - sum_{s' in head} a[s'] da[s'])
+//   dg[sh]  += r_j dsim[sh] t_j ;  dG[sh] -= r_j dsim[sh] mu_j ;  dc0[sh] += dsim[sh]
+//   dr = sum_sh dsim[sh] e[sh] + a[sh] f[sh] ;  dmu = r_j sum_sh (a[sh] dm[sh] - dsim[sh] G[sh])
+//   dt_j = sum_sh (r_j dsim[sh]) g[sh] + (r_j a[sh]) dU[sh]  +  dmu/D  -  dr r_j^3 (t_j - mu_j)/D
+// Same tile ring / phase structure as the forward; phase 2 (thread <-> 4 channels) keeps its g / dU columns in registers,
+// produces dt_j with coalesced 16-byte accesses (optionally accumulating onto the gradient of earlier layers) and
+// accumulates dg in registers.
+template <int HS>
+struct SlotBwdCfg {
+  static constexpr int STAGES = (HS <= 8) ? 3 : 2;
+  static constexpr int OFF_TILE = 0;
+  static constexpr int OFF_G = STAGES * kSTileBytes;                 // g[HS][768]
+  static constexpr int OFF_DU = OFF_G + HS * kSD * 4;                // dU[HS][768]
+  static constexpr int OFF_PART = OFF_DU + HS * kSD * 4;             // partial[8 warps][16 tokens][2 HS]
+  static constexpr int OFF_COEF = OFF_PART + 8 * kST * 2 * HS * 4;   // coef[16 tokens][2 HS + 4]: alpha[HS], beta[HS], kappa, lambda
+  static constexpr int COEF_STRIDE = 2 * HS + 4;
+  static constexpr int OFF_ACC = OFF_COEF + kST * COEF_STRIDE * 4;   // running dG / dc0 partials [2][16][HS]
+  static constexpr int OFF_BAR = OFF_ACC + 2 * kST * HS * 4;
+  static constexpr int BYTES = OFF_BAR + 64 + 1024;
+};
+
+struct SlotBwdParams {
+  int B, N, S;
+  int tiles_per_cta, tiles_per_clip;
+  const float* mu; const float* rstd;     // [B, N]
+  const float* g; const float* G;         // [B, HS, 768], [B, HS]
+  const float* a;                         // [B, HS, N]
+  const float* dU; const float* dm; const float* dA;   // [B, HS, 768], [B, HS], [B, HS]
+  const float* dattn;                     // [B, HS, N] or null
+  float* dt; int accumulate;              // [B, N, 768]
+  float* dg; float* dG; float* dc0;       // (+=)
+};
+
+template <int HS>
+__global__ void __launch_bounds__(kSlotThreads, 1)
+slot_stream_bwd_kernel(const __grid_constant__ CUtensorMap tmTok, const SlotBwdParams p) {
+  using Cfg = SlotBwdCfg<HS>;
+  constexpr int S = HS / 4;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* g_s = reinterpret_cast<float*>(smem + Cfg::OFF_G);
+  float* du_s = reinterpret_cast<float*>(smem + Cfg::OFF_DU);
+  float* part = reinterpret_cast<float*>(smem + Cfg::OFF_PART);
+  float* coef = reinterpret_cast<float*>(smem + Cfg::OFF_COEF);
+  float* accG = reinterpret_cast<float*>(smem + Cfg::OFF_ACC);
+  float* accC = accG + kST * HS;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.y;
+  const int tile0 = blockIdx.x * p.tiles_per_cta;
+  const int ntiles = min(p.tiles_per_cta, p.tiles_per_clip - tile0);
+  if (ntiles <= 0) return;
+
+  if (tid == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) mbar_init(&full[s], 1);
+    fence_barrier_init();
+  }
+  {
+    const float4* sg = reinterpret_cast<const float4*>(p.g + (long long)b * HS * kSD);
+    const float4* sd = reinterpret_cast<const float4*>(p.dU + (long long)b * HS * kSD);
+    for (int i = tid; i < HS * kSD / 4; i += kSlotThreads) {
+      reinterpret_cast<float4*>(g_s)[i] = __ldg(sg + i);
+      reinterpret_cast<float4*>(du_s)[i] = __ldg(sd + i);
+    }
+    for (int i = tid; i < 2 * kST * HS; i += kSlotThreads) accG[i] = 0.f;
+  }
+  __syncthreads();
+
+  auto issue = [&](int it) {
+    const int st = it % Cfg::STAGES;
+    mbar_arrive_expect_tx(&full[st], kSTileBytes);
+    uint8_t* dst = smem + Cfg::OFF_TILE + st * kSTileBytes;
+    const int tok0 = (tile0 + it) * kST;
+#pragma unroll 1
+    for (int bx = 0; bx < kSBoxes; ++bx) tma_load_3d(dst + bx * (kST * 128), &tmTok, &full[st], bx * 32, tok0, b);
+  };
+  if (tid == 0) {
+    for (int it = 0; it < Cfg::STAGES - 1 && it < ntiles; ++it) issue(it);
+  }
+
+  const uint32_t g_u = smem_u32(g_s), du_u = smem_u32(du_s), coef_u = smem_u32(coef);
+  // phase-2 state: thread t < 192 owns channels [4t, 4t+4): its g / dU columns and the dg accumulators
+  float4 gr[HS], dur[HS], dgacc[HS];
+  if (tid < kSD / 4) {
+#pragma unroll
+    for (int i = 0; i < HS; ++i) {
+      gr[i] = lds128(g_u + (i * kSD + tid * 4) * 4);
+      dur[i] = lds128(du_u + (i * kSD + tid * 4) * 4);
+      dgacc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  const float* Gs = p.G + b * HS;
+  const float* dms = p.dm + b * HS;
+  const float* dAs = p.dA + b * HS;
+
+  const int tok_l = lane & 15, half = lane >> 4;
+  const int slice = warp * 2 + half;
+  for (int it = 0; it < ntiles; ++it) {
+    const int st = it % Cfg::STAGES;
+    if (tid == 0 && it + Cfg::STAGES - 1 < ntiles) issue(it + Cfg::STAGES - 1);
+    mbar_wait(&full[st], (it / Cfg::STAGES) & 1);
+    const uint32_t tile = smem_u32(smem + Cfg::OFF_TILE + st * kSTileBytes);
+    const int tok_base = (tile0 + it) * kST;
+
+    // ---------------- phase 1: g . t and dU . t over this lane's 48 channels
+    {
+      float dg_[HS], df_[HS];
+#pragma unroll
+      for (int i = 0; i < HS; ++i) { dg_[i] = 0.f; df_[i] = 0.f; }
+#pragma unroll 2
+      for (int c = 0; c < 12; ++c) {
+        const int c4 = slice * 12 + c;
+        const float4 t = lds128(tile_chunk(tile, tok_l, c4));
+#pragma unroll
+        for (int i = 0; i < HS; ++i) {
+          const float4 gv = lds128(g_u + (i * kSD + c4 * 4) * 4);
+          const float4 dv_ = lds128(du_u + (i * kSD + c4 * 4) * 4);
+          dg_[i] = fmaf(t.x, gv.x, fmaf(t.y, gv.y, fmaf(t.z, gv.z, fmaf(t.w, gv.w, dg_[i]))));
+          df_[i] = fmaf(t.x, dv_.x, fmaf(t.y, dv_.y, fmaf(t.z, dv_.z, fmaf(t.w, dv_.w, df_[i]))));
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < HS; ++i) {
+        dg_[i] += __shfl_xor_sync(0xffffffffu, dg_[i], 16);
+        df_[i] += __shfl_xor_sync(0xffffffffu, df_[i], 16);
+      }
+      if (half == 0) {
+        float* pp = part + (warp * kST + tok_l) * (2 * HS);
+#pragma unroll
+        for (int i = 0; i < HS; ++i) { pp[i] = dg_[i]; pp[HS + i] = df_[i]; }
+      }
+    }
+    __syncthreads();
+    // ---------------- phase 1b: warp 0, lanes 0..15 <-> tokens: per-token coefficients
+    if (warp == 0 && lane < kST) {
+      float e[HS], f[HS];
+#pragma unroll
+      for (int i = 0; i < HS; ++i) { e[i] = 0.f; f[i] = 0.f; }
+#pragma unroll 2
+      for (int sl = 0; sl < 8; ++sl) {
+        const float* pp = part + (sl * kST + lane) * (2 * HS);
+#pragma unroll
+        for (int i = 0; i < HS; ++i) { e[i] += pp[i]; f[i] += pp[HS + i]; }
+      }
+      const int tok = tok_base + lane;
+      const bool valid = tok < p.N;
+      const float mu = valid ? __ldg(p.mu + (long long)b * p.N + tok) : 0.f;
+      const float r = valid ? __ldg(p.rstd + (long long)b * p.N + tok) : 0.f;
+      float dr = 0.f, dmu = 0.f;
+      float* cf = coef + lane * Cfg::COEF_STRIDE;
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        float av[S], da[S];
+        float dot = 0.f;
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          const int i = h * S + s;
+          av[s] = valid ? __ldg(p.a + ((long long)b * HS + i) * p.N + tok) : 0.f;
+          e[i] -= mu * __ldg(Gs + i);
+          f[i] += mu * __ldg(dms + i);
+          da[s] = fmaf(r, f[i], __ldg(dAs + i));
+          if (p.dattn != nullptr && valid) da[s] += __ldg(p.dattn + ((long long)b * HS + i) * p.N + tok);
+          dot = fmaf(av[s], da[s], dot);
+        }
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          const int i = h * S + s;
+          const float dsim = av[s] * (da[s] - dot);
+          dr += dsim * e[i] + av[s] * f[i];
+          dmu += av[s] * __ldg(dms + i) - dsim * __ldg(Gs + i);
+          const float alpha = r * dsim;
+          cf[i] = alpha;
+          cf[HS + i] = r * av[s];
+          accG[lane * HS + i] -= alpha * mu;
+          accC[lane * HS + i] += dsim;
+        }
+      }
+      dmu *= r;
+      const float lambda = -dr * r * r * r * (1.0f / kSD);
+      cf[2 * HS] = dmu * (1.0f / kSD) - lambda * mu;   // kappa'
+      cf[2 * HS + 1] = lambda;
+    }
+    __syncthreads();
+    // ---------------- phase 2: dt_j and dg accumulation, thread <-> 4 channels
+    if (tid < kSD / 4) {
+#pragma unroll 2
+      for (int j = 0; j < kST; ++j) {
+        const int tok = tok_base + j;
+        if (tok >= p.N) break;
+        const float4 t = lds128(tile_chunk(tile, j, tid));
+        const uint32_t cj = coef_u + j * Cfg::COEF_STRIDE * 4;
+        const float2 kl = lds64(cj + 2 * HS * 4);
+        float4 o = make_float4(fmaf(kl.y, t.x, kl.x), fmaf(kl.y, t.y, kl.x), fmaf(kl.y, t.z, kl.x), fmaf(kl.y, t.w, kl.x));
+        float* dst = p.dt + ((long long)b * p.N + tok) * kSD + tid * 4;
+        float4 old = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.accumulate) old = *reinterpret_cast<const float4*>(dst);
+#pragma unroll
+        for (int i4 = 0; i4 < HS / 4; ++i4) {
+          const float4 al = lds128(cj + 16 * i4);
+          const float4 be = lds128(cj + HS * 4 + 16 * i4);
+          const float alv[4] = {al.x, al.y, al.z, al.w};
+          const float bev[4] = {be.x, be.y, be.z, be.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = 4 * i4 + u;
+            o.x = fmaf(alv[u], gr[i].x, fmaf(bev[u], dur[i].x, o.x));
+            o.y = fmaf(alv[u], gr[i].y, fmaf(bev[u], dur[i].y, o.y));
+            o.z = fmaf(alv[u], gr[i].z, fmaf(bev[u], dur[i].z, o.z));
+            o.w = fmaf(alv[u], gr[i].w, fmaf(bev[u], dur[i].w, o.w));
+            dgacc[i].x = fmaf(alv[u], t.x, dgacc[i].x); dgacc[i].y = fmaf(alv[u], t.y, dgacc[i].y);
+            dgacc[i].z = fmaf(alv[u], t.z, dgacc[i].z); dgacc[i].w = fmaf(alv[u], t.w, dgacc[i].w);
+          }
+        }
+        o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+        *reinterpret_cast<float4*>(dst) = o;
+      }
+    }
+    __syncthreads();
+  }
+  if (tid < kSD / 4) {
+    float* dst = p.dg + (long long)b * HS * kSD + tid * 4;
+#pragma unroll
+    for (int i = 0; i < HS; ++i) red_add_v4_f32(dst + i * kSD, dgacc[i].x, dgacc[i].y, dgacc[i].z, dgacc[i].w);
+  }
+  if (tid < HS) {
+    float a = 0.f, c = 0.f;
+#pragma unroll
+    for (int j = 0; j < kST; ++j) { a += accG[j * HS + tid]; c += accC[j * HS + tid]; }
+    atomicAdd(p.dG + b * HS + tid, a);
+    atomicAdd(p.dc0 + b * HS + tid, c);
+  }
+}
+
+template <int HS>
+static int launch_slot_bwd(const CUtensorMap& tm, const SlotBwdParams& p, int splits, cudaStream_t s) {
+  using Cfg = SlotBwdCfg<HS>;
+  static_assert(Cfg::BYTES <= 227 * 1024, "slot backward does not fit in shared memory");
+  auto kern = slot_stream_bwd_kernel<HS>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    DV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::BYTES));
+    attr_done = true;
+  }
+  const double bytes = (double)p.B * p.N * kSD * 4 * (p.accumulate ? 3.0 : 2.0);
+  const int prof = prof_begin(DEVIAS_PROF_SLOT, bytes, s);
+  kern<<<dim3(splits, p.B), kSlotThreads, Cfg::BYTES, s>>>(tm, p);
+  prof_end(prof, s);
+  DV_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return DEVIAS_OK;
+}
+
 static int make_token_tmap(CUtensorMap* tm, const float* tokens, int B, int N) {
   const uint64_t dims[3] = {(uint64_t)kSD, (uint64_t)N, (uint64_t)B};
   const uint64_t str[2] = {(uint64_t)kSD * 4, (uint64_t)N * kSD * 4};
@@ -288,4 +545,33 @@ extern "C" int devias_slot_stream_fwd(const float* tokens, const float* g, const
     case 4: return launch_slot_fwd<16>(tm, p, splits, s);
     default: return launch_slot_fwd<32>(tm, p, splits, s);
   }
+}
+
+extern "C" int devias_slot_stream_bwd(const float* tokens, const float* mu, const float* rstd, const float* g, const float* G,
+                                      const float* attn, const float* dU, const float* dm, const float* dA, const float* dattn,
+                                      float* dtokens, int accumulate_dtokens, float* dg, float* dG, float* dc0, int batch,
+                                      int n_tokens, int dim, int num_slots, void* stream) {
+  using namespace dv;
+  DV_REQUIRE(tokens && mu && rstd && g && G && attn && dU && dm && dA && dtokens && dg && dG && dc0, "null pointer");
+  DV_REQUIRE(dim == kSD, "token dim must be 768");
+  if (num_slots != 2 && num_slots != 4) {
+    set_last_error("num_slots", "the streaming backward is instantiated for 2 and 4 slots (g and dU must fit in shared memory)",
+                   __FILE__, __LINE__);
+    return DEVIAS_ERR_UNSUPPORTED;
+  }
+  DV_REQUIRE(batch > 0 && n_tokens > 0, "empty problem");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CUtensorMap tm;
+  int rc = make_token_tmap(&tm, tokens, batch, n_tokens);
+  if (rc) return rc;
+  const int tiles = (n_tokens + kST - 1) / kST;
+  int splits = (2 * sm_count() + batch - 1) / batch;
+  if (splits > (tiles + 3) / 4) splits = (tiles + 3) / 4;
+  if (splits < 1) splits = 1;
+  const int per = (tiles + splits - 1) / splits;
+  splits = (tiles + per - 1) / per;
+  SlotBwdParams p{batch, n_tokens, num_slots, per, tiles, mu, rstd, g, G, attn, dU, dm, dA, dattn, dtokens, accumulate_dtokens,
+                  dg, dG, dc0};
+  if (num_slots == 2) return launch_slot_bwd<8>(tm, p, splits, s);
+  return launch_slot_bwd<16>(tm, p, splits, s);
 }

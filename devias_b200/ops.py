@@ -175,10 +175,8 @@ def slot_stream_fwd(tokens, g, G, c0, want_attn=True, want_stats=True, eps=1e-5)
     B, N, D = tokens.shape
     HS = g.shape[1]
     dev = tokens.device
-    acc = torch.zeros(B, HS, D + 2, device=dev, dtype=torch.float32)   # one memset for U | m | A
     U = torch.zeros(B, HS, D, device=dev, dtype=torch.float32)
     mA = torch.zeros(2, B, HS, device=dev, dtype=torch.float32)
-    del acc
     attn = torch.empty(B, HS, N, device=dev, dtype=torch.float32) if want_attn else None
     mu = torch.empty(B, N, device=dev, dtype=torch.float32) if want_stats else None
     rstd = torch.empty(B, N, device=dev, dtype=torch.float32) if want_stats else None
@@ -187,3 +185,24 @@ def slot_stream_fwd(tokens, g, G, c0, want_attn=True, want_stats=True, eps=1e-5)
                                            float(eps), _stream())
     _lib.check(rc, 'slot_stream_fwd')
     return U, mA[0], mA[1], attn, mu, rstd
+
+
+def slot_stream_bwd(tokens, mu, rstd, g, G, attn, dU, dm, dA, dattn=None, dtokens=None):
+    """-> (dtokens, dg, dG, dc0); when `dtokens` is given the token gradient is accumulated into it in place"""
+    _need_cuda(tokens, g, dU)
+    B, N, D = tokens.shape
+    HS = g.shape[1]
+    dev = tokens.device
+    acc = dtokens is not None
+    if dtokens is None:
+        dtokens = torch.empty_like(tokens)
+    dg = torch.zeros(B, HS, D, device=dev, dtype=torch.float32)
+    dGc = torch.zeros(2, B, HS, device=dev, dtype=torch.float32)
+    cont = lambda t: None if t is None else t.contiguous()
+    dU, dm, dA, dattn = cont(dU), cont(dm), cont(dA), cont(dattn)
+    rc = _lib.lib().devias_slot_stream_bwd(tokens.data_ptr(), mu.data_ptr(), rstd.data_ptr(), g.data_ptr(), G.data_ptr(),
+                                           attn.data_ptr(), dU.data_ptr(), dm.data_ptr(), dA.data_ptr(), _ptr(dattn),
+                                           dtokens.data_ptr(), int(acc), dg.data_ptr(), dGc[0].data_ptr(), dGc[1].data_ptr(),
+                                           B, N, D, HS // 4, _stream())
+    _lib.check(rc, 'slot_stream_bwd')
+    return dtokens, dg, dGc[0], dGc[1]

@@ -43,7 +43,7 @@ def slot_stream_torch(tokens, mu, r, g, G, c0):
     return U, m, A, a
 
 
-def slot_attention_layer(x, tokens, mu, r, p, stream=slot_stream_torch):
+def slot_attention_layer(x, tokens, mu, r, p, stream=slot_stream_torch, **stream_kw):
     """One `PreNorm(Attention)` application on slots x [B,S,D] against tokens [B,N,D].
     p: dict with norm_w/b (slots LN), ctx_w/b (context LN), wq, wk, wv [2048,768], wo [768,2048], bo.
     Returns (to_out(attn.v) [B,S,D], sim_distill [(B*4), S, N])."""
@@ -56,7 +56,7 @@ def slot_attention_layer(x, tokens, mu, r, p, stream=slot_stream_torch):
     g = (qt * p['ctx_w']).reshape(B, H * S, D)
     G = g.sum(-1)
     c0 = (qt @ p['ctx_b']).reshape(B, H * S)
-    U, m, A, a = stream(tokens, mu, r, g.contiguous(), G.contiguous(), c0.contiguous())
+    U, m, A, a = stream(tokens, mu, r, g.contiguous(), G.contiguous(), c0.contiguous(), **stream_kw)
     cbar = (p['ctx_w'] * (U - m.unsqueeze(-1)) + p['ctx_b'] * A.unsqueeze(-1)) / (A.unsqueeze(-1) + 1e-7)
     out = torch.einsum('bhsc,hdc->bshd', cbar.view(B, H, S, D), p['wv'].view(H, dh, D)).reshape(B, S, H * dh)
     return F.linear(out, p['wo'], p['bo']), a.reshape(B * H, S, -1)

@@ -1,7 +1,6 @@
-"""CUDA side of the streaming slot attention (contract: devias_b200/slot_attention.py).
-
-Forward: csrc/slot_attn.cu (one pass over the tokens per layer).  Backward (round 1): the same folded expressions
-differentiated by autograd on the GPU from the saved inputs (INTERIM until the streaming backward kernel lands)."""
+"""CUDA side of the streaming slot attention (contract: devias_b200/slot_attention.py): csrc/slot_attn.cu forward and
+backward.  The gradient w.r.t. the context tokens is summed over the layers of the aggregation block IN PLACE: every
+layer's backward kernel accumulates into one shared buffer and only the last one to run hands it to autograd."""
 import torch
 
 from . import ops
@@ -13,25 +12,64 @@ def token_stats(tokens: torch.Tensor, eps: float = 1e-5):
     return None, None
 
 
+class _TokenGradSink:
+    """shared by the `depth` SlotStreamFn nodes of one AggregationBlock.forward call"""
+
+    def __init__(self):
+        self.pending = 0
+        self.buf = None
+
+
 class SlotStreamFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, tokens, g, G, c0):
-        U, m, A, attn, mu, rstd = ops.slot_stream_fwd(tokens.contiguous(), g.contiguous(), G.contiguous(), c0.contiguous())
-        ctx.save_for_backward(tokens, g, G, c0)
+    def forward(ctx, tokens, g, G, c0, sink):
+        tokens, g, G, c0 = tokens.contiguous(), g.contiguous(), G.contiguous(), c0.contiguous()
+        U, m, A, attn, mu, rstd = ops.slot_stream_fwd(tokens, g, G, c0)
+        ctx.save_for_backward(tokens, g, G, attn, mu, rstd)
+        ctx.c0 = c0
+        ctx.sink = sink
+        ctx.cuda_bwd = g.shape[1] in (8, 16)
+        if sink is not None:
+            sink.pending += 1
+        ctx.mark_non_differentiable(mu, rstd)
         return U, m, A, attn
 
     @staticmethod
     def backward(ctx, dU, dm, dA, dattn):
-        tokens, g, G, c0 = ctx.saved_tensors
-        with torch.enable_grad():
-            leaves = [t.detach().requires_grad_(True) for t in (tokens, g, G, c0)]
-            mu, r = SA.token_stats(leaves[0])
-            outs = SA.slot_stream_torch(leaves[0], mu, r, *leaves[1:])
-            grads = torch.autograd.grad(outs, leaves, [dU, dm, dA, dattn], allow_unused=True)
-        return tuple(grads)
+        tokens, g, G, attn, mu, rstd = ctx.saved_tensors
+        zeros = lambda ref: torch.zeros_like(ref)
+        dU = zeros(g) if dU is None else dU
+        dm = zeros(G) if dm is None else dm
+        dA = zeros(G) if dA is None else dA
+        if not ctx.cuda_bwd:
+            # S = 8 (micro-benchmark configuration only): g and dU do not fit in shared memory next to the token ring;
+            # the same folded expressions are differentiated by autograd on the GPU.
+            with torch.enable_grad():
+                leaves = [t.detach().requires_grad_(True) for t in (tokens, g, G, ctx.c0)]
+                mu2, r2 = SA.token_stats(leaves[0])
+                outs = SA.slot_stream_torch(leaves[0], mu2, r2, leaves[1], leaves[2], leaves[3])
+                go = [dU, dm, dA, zeros(attn) if dattn is None else dattn]
+                grads = torch.autograd.grad(outs, leaves, go, allow_unused=True)
+            return grads[0], grads[1], grads[2], grads[3], None
+        sink = ctx.sink
+        need_dt = ctx.needs_input_grad[0]
+        if sink is not None and need_dt:
+            dt, dg, dG, dc0 = ops.slot_stream_bwd(tokens, mu, rstd, g, G, attn, dU, dm, dA, dattn, dtokens=sink.buf)
+            sink.buf = dt
+            sink.pending -= 1
+            out_dt = None
+            if sink.pending == 0:
+                out_dt, sink.buf = sink.buf, None
+            return out_dt, dg, dG, dc0, None
+        dt, dg, dG, dc0 = ops.slot_stream_bwd(tokens, mu, rstd, g, G, attn, dU, dm, dA, dattn)
+        return (dt if need_dt else None), dg, dG, dc0, None
 
 
-def slot_stream(tokens, mu, r, g, G, c0):
+def new_sink():
+    return _TokenGradSink()
+
+
+def slot_stream(tokens, mu, r, g, G, c0, sink=None):
     if tokens.dtype != torch.float32:
         tokens = tokens.float()
-    return SlotStreamFn.apply(tokens, g, G, c0)
+    return SlotStreamFn.apply(tokens, g, G, c0, sink)

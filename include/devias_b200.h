@@ -90,6 +90,14 @@ int devias_slot_stream_fwd(const float* tokens, const float* g, const float* G, 
                            float* attn, float* mu, float* rstd, int batch, int n_tokens, int dim, int num_slots, float eps,
                            void* stream);
 
+/* Backward of devias_slot_stream_fwd.  attn / mu / rstd are the forward's outputs; dU, dm, dA (and optionally dattn) the
+ * upstream gradients.  Writes dtokens [batch, n_tokens, 768] (accumulate_dtokens != 0: +=, used to sum the layers of the
+ * aggregation block in place) and ACCUMULATES dg [batch, 4*S, 768], dG, dc0 [batch, 4*S].  S in {2, 4}. */
+int devias_slot_stream_bwd(const float* tokens, const float* mu, const float* rstd, const float* g, const float* G,
+                           const float* attn, const float* dU, const float* dm, const float* dA, const float* dattn,
+                           float* dtokens, int accumulate_dtokens, float* dg, float* dG, float* dc0, int batch, int n_tokens,
+                           int dim, int num_slots, void* stream);
+
 /* dtype ids for entry points that accept several input element types */
 #define DEVIAS_DTYPE_F32 0
 #define DEVIAS_DTYPE_BF16 1

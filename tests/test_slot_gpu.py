@@ -29,3 +29,38 @@ def test_slot_stream_fwd(B, N, S):
     assert_close(U, rU, 1e-5, 'U')
     # slot-axis softmax: the S probabilities of every head sum to one for every token
     assert torch.allclose(attn.view(B, 4, S, N).sum(2), torch.ones(B, 4, N, device='cuda'), atol=1e-5)
+
+
+@pytest.mark.parametrize('B,N,S,with_dattn', [(2, 1568, 2, True), (3, 1568, 4, False), (2, 100, 2, True), (1, 1569, 2, False)])
+def test_slot_stream_bwd(B, N, S, with_dattn):
+    """streaming backward kernel vs float64 autograd of the same folded contract"""
+    from devias_b200 import ops, slot_attention as SA
+    HS = 4 * S
+    gen = torch.Generator(device='cuda').manual_seed(7 + S)
+    tok = O.synth_tokens(B, n_tokens=N, seed=3 * B + N).cuda() + 0.25
+    g = torch.randn(B, HS, 768, device='cuda', generator=gen) * 0.05
+    G = g.sum(-1).contiguous()
+    c0 = torch.randn(B, HS, device='cuda', generator=gen) * 0.3
+    dU = torch.randn(B, HS, 768, device='cuda', generator=gen)
+    dm = torch.randn(B, HS, device='cuda', generator=gen)
+    dA = torch.randn(B, HS, device='cuda', generator=gen)
+    dattn = torch.randn(B, HS, N, device='cuda', generator=gen) if with_dattn else None
+    U, m, A, attn, mu, rstd = ops.slot_stream_fwd(tok, g, G, c0)
+    dt, dg, dG, dc0 = ops.slot_stream_bwd(tok, mu, rstd, g, G, attn, dU, dm, dA, dattn)
+    leaves = [t.double().requires_grad_(True) for t in (tok, g, G, c0)]
+    rmu, rr = SA.token_stats(leaves[0])
+    # token_stats upcasts to float internally for float32 inputs only; recompute in float64 here
+    t64 = leaves[0]
+    rmu = t64.mean(-1); rr = torch.rsqrt((t64 - rmu.unsqueeze(-1)).square().mean(-1) + 1e-5)
+    outs = SA.slot_stream_torch(t64, rmu, rr, leaves[1], leaves[2], leaves[3])
+    go = [dU.double(), dm.double(), dA.double(), (dattn.double() if with_dattn else torch.zeros_like(outs[3]))]
+    rdt, rdg, rdG, rdc0 = torch.autograd.grad(outs, leaves, go)
+    assert_close(dt, rdt, 2e-5, 'd tokens')
+    assert_close(dg, rdg, 2e-5, 'dg')
+    assert_close(dG, rdG, 2e-5, 'dG')
+    assert_close(dc0, rdc0, 2e-5, 'dc0')
+    # in-place accumulation across layers
+    base = torch.randn_like(tok)
+    acc = base.clone()
+    ops.slot_stream_bwd(tok, mu, rstd, g, G, attn, dU, dm, dA, dattn, dtokens=acc)
+    assert_close(acc, base.double() + rdt, 2e-5, 'accumulated d tokens')
