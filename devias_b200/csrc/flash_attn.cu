@@ -54,8 +54,7 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint64_t* s_empty = bars + 9;            // 2
   uint64_t* p_full = bars + 11;            // 2
   uint64_t* p_empty = bars + 13;           // 2
-  uint64_t* o_full = bars + 15;            // 2
-  uint64_t* o_empty = bars + 17;           // 2
+  uint64_t* pv_done = bars + 15;           // 1: completes once per key tile, after P_j V_j has been accumulated into O
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
 
   const int warp = threadIdx.x >> 5;
@@ -78,8 +77,8 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       for (int i = 0; i < 2; ++i) {
         mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4);
         mbar_init(&p_full[i], 4); mbar_init(&p_empty[i], 1);
-        mbar_init(&o_full[i], 1); mbar_init(&o_empty[i], 4);
       }
+      mbar_init(pv_done, 1);
       fence_barrier_init();
     }
     __syncwarp();
@@ -90,7 +89,7 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t tm_s[2] = {tmem, tmem + 64};
-  const uint32_t tm_o[2] = {tmem + 128, tmem + 192};
+  const uint32_t tm_o = tmem + 128;        // running (unnormalised) output, accumulated by the MMAs across key tiles
 
   if (warp == 0) {
     if (elect_one()) {
@@ -126,14 +125,13 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       for (int j = 0; j < T; ++j) {
         if (j + 1 < T) issue_s(j + 1);
         const int st = j % kKVStages;
-        mbar_wait(&p_full[j & 1], (j >> 1) & 1);
-        mbar_wait(&o_empty[j & 1], ((j >> 1) & 1) ^ 1);
+        mbar_wait(&p_full[j & 1], (j >> 1) & 1);   // P_j is in smem and any rescaling of O (tcgen05.st) has been fenced
         tc_fence_after();
         const uint64_t da = umma_desc_sw128(smem_u32(smem + FaSmem::OFF_P + (j & 1) * FaSmem::P_BYTES), 0, 1024);
         const uint64_t db = umma_desc_sw128(smem_u32(smem + FaSmem::OFF_V + st * FaSmem::V_BYTES), kKT * 128, 1024);
 #pragma unroll
-        for (int k = 0; k < kKT / 16; ++k) umma_ss(tm_o[j & 1], da + 2 * k, db + 128 * k, idesc_o, k > 0 ? 1u : 0u);
-        umma_commit(&o_full[j & 1]);
+        for (int k = 0; k < kKT / 16; ++k) umma_ss(tm_o, da + 2 * k, db + 128 * k, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+        umma_commit(pv_done);
         umma_commit(&kv_empty[st]);
         umma_commit(&p_empty[j & 1]);
       }
@@ -144,11 +142,11 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const int lane = (int)lane_id();
     const int r = q * 32 + lane;                     // query row inside the tile == TMEM lane
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    // Lazy rescaling: exponentials are taken relative to a reference maximum `m` that is only moved (and the TMEM
+    // accumulator rescaled) when the running maximum exceeds it by more than 8 (log2 units), i.e. P <= 256.
     float m = -INFINITY, l = 0.f;
-    float o[kHD];
-#pragma unroll
-    for (int i = 0; i < kHD; ++i) o[i] = 0.f;
     const uint32_t p_row_base = smem_u32(smem + FaSmem::OFF_P + r * 128);
+    const uint64_t cc = f2_pack(p.scale_log2, p.scale_log2);
     for (int j = 0; j < T; ++j) {
       mbar_wait(&s_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
@@ -170,61 +168,66 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       float mx = -INFINITY;
 #pragma unroll
       for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(s0[i]), __uint_as_float(s1[i])));
-      const float m_new = fmaxf(m, mx * p.scale_log2);   // scale > 0: max(c s) = c max(s)
-      const float alpha = fast_exp2(m - m_new);
-      m = m_new;
+      const float m_run = fmaxf(m, mx * p.scale_log2);   // scale > 0: max(c s) = c max(s)
+      // observe EVERY phase of pv_done in order (a parity wait can only tell the current phase from the previous one);
+      // by now P_{j-1} V_{j-1}, issued right after the previous iteration, has normally retired already
+      if (j > 0) mbar_wait(pv_done, (j - 1) & 1);
+      if (__any_sync(0xffffffffu, m_run > m + 8.0f)) {
+        const float alpha = fast_exp2(m - m_run);       // 0 on the first tile (m = -inf)
+        if (j > 0) {
+          tc_fence_after();
+#pragma unroll
+          for (int hlf = 0; hlf < 2; ++hlf) {
+            uint32_t t[32];
+            tmem_ld_32x32b_x32(tm_o + lane_sel + 32 * hlf, t);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * alpha);
+            tmem_st_32x32b_x32(tm_o + lane_sel + 32 * hlf, t);
+          }
+          tmem_st_wait();
+        }
+        l *= alpha;
+        m = m_run;
+      }
+      const uint64_t negm = f2_pack(-m, -m);
       // P_j -> smem (K-major, 128B swizzle: 16-byte chunk c of row r lands at chunk c ^ (r & 7))
-      mbar_wait(&p_empty[j & 1], ((j >> 1) & 1) ^ 1);
+      mbar_wait(&p_empty[j & 1], ((j >> 1) & 1) ^ 1);     // (implied by pv_done(j-1); kept as the explicit buffer hand-off)
       const uint32_t prow = p_row_base + (j & 1) * FaSmem::P_BYTES;
-      float sum = 0.f;
+      uint64_t sum2 = 0ull;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        float e[8];
+      for (int c = 0; c < 8; ++c) {
+        uint32_t pk[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { e[i] = fast_exp2(fmaf(__uint_as_float(s0[8 * c + i]), p.scale_log2, -m_new)); sum += e[i]; }
-        sts128(prow + ((c ^ (r & 7)) << 4), pack_bf16(e[0], e[1]), pack_bf16(e[2], e[3]), pack_bf16(e[4], e[5]), pack_bf16(e[6], e[7]));
+        for (int i = 0; i < 4; ++i) {
+          const int e = 8 * (c & 3) + 2 * i;
+          const uint64_t x = c < 4 ? f2_pack(__uint_as_float(s0[e]), __uint_as_float(s0[e + 1]))
+                                   : f2_pack(__uint_as_float(s1[e]), __uint_as_float(s1[e + 1]));
+          const uint64_t y = f2_fma(x, cc, negm);
+          const float e0 = fast_exp2(f2_lo(y)), e1 = fast_exp2(f2_hi(y));
+          sum2 = f2_add(sum2, f2_pack(e0, e1));
+          pk[i] = pack_bf16(e0, e1);
+        }
+        sts128(prow + ((c ^ (r & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
       }
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        float e[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { e[i] = fast_exp2(fmaf(__uint_as_float(s1[8 * c + i]), p.scale_log2, -m_new)); sum += e[i]; }
-        sts128(prow + (((c + 4) ^ (r & 7)) << 4), pack_bf16(e[0], e[1]), pack_bf16(e[2], e[3]), pack_bf16(e[4], e[5]),
-               pack_bf16(e[6], e[7]));
-      }
-      l = l * alpha + sum;
+      l += f2_lo(sum2) + f2_hi(sum2);
       fence_proxy_async();
+      tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[j & 1]);
-      // fold the previous tile's P V product into the running output, then rescale to the new maximum
-      if (j > 0) {
-        mbar_wait(&o_full[(j - 1) & 1], ((j - 1) >> 1) & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int hlf = 0; hlf < 2; ++hlf) {
-          uint32_t t[32];
-          tmem_ld_32x32b_x32(tm_o[(j - 1) & 1] + lane_sel + 32 * hlf, t);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o[32 * hlf + i] = (o[32 * hlf + i] + __uint_as_float(t[i])) * alpha;
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&o_empty[(j - 1) & 1]);
-      }
     }
+    float o[kHD];
     {
-      const int j = T - 1;
-      mbar_wait(&o_full[j & 1], (j >> 1) & 1);
+      mbar_wait(pv_done, (T - 1) & 1);
       tc_fence_after();
       const float inv = 1.0f / l;
 #pragma unroll
       for (int hlf = 0; hlf < 2; ++hlf) {
         uint32_t t[32];
-        tmem_ld_32x32b_x32(tm_o[j & 1] + lane_sel + 32 * hlf, t);
+        tmem_ld_32x32b_x32(tm_o + lane_sel + 32 * hlf, t);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o[32 * hlf + i] = (o[32 * hlf + i] + __uint_as_float(t[i])) * inv;
+        for (int i = 0; i < 32; ++i) o[32 * hlf + i] = __uint_as_float(t[i]) * inv;
       }
     }
     const int qi = q0 + r;
@@ -250,13 +253,13 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
 // =====================================================================================================================
 // Backward.  One CTA per (clip, head, 128-key tile); loop over 128-query tiles.  dK/dV accumulate in TMEM for the whole
-// loop; each iteration's dQ partial goes TMEM -> red.global.add.f32 into an fp32 [B*N, H*64] buffer (L2 resident).
-//   S^T = K Q_i^T, dP^T = V dO_i^T            (TMEM, thread = key row)
-//   P^T = exp2(c S^T - lse2[q]),  dS^T = P^T * (dP^T - delta[q])      -> bf16 -> smem (K-major over q, 128B swizzle)
-//   dV += P^T dO_i,  dK += dS^T Q_i,  dQ_i = dS K   (the dS^T tile is re-read as an MN-major A operand)
+// loop; each iteration's dQ partial goes TMEM -> smem -> TMA reduce-add into an fp32 [B, N, H*64] buffer (L2 resident).
+//   S = Q_i K^T, dP = dO_i V^T                 (TMEM, thread = query row, so lse2[q] / delta[q] are per-thread scalars)
+//   P = exp2(c S - lse2[q]),  dS = P * (dP - delta[q])       -> bf16 -> smem, K-major over the keys (128B swizzle)
+//   dV += P^T dO_i,  dK += dS^T Q_i   (the P / dS tiles are read as MN-major A operands),   dQ_i = dS K
 // The softmax scale is applied to dK in the epilogue and to dQ in the fp32 -> bf16 conversion kernel.
-//   warp 0 : TMA (K,V once; Q_i, dO_i, lse2_i, delta_i through a 2-stage ring)   warp 1 : tcgen05 issuer
-//   warps 2..9 : compute (lane quarter = warp % 4, column half = (warp - 2) / 4)
+//   warp 0 : TMA (K,V once; Q_i, dO_i through a 2-stage ring)   warp 1 : tcgen05 issuer
+//   warps 2..9 : compute (query-row quarter = warp % 4, key-column half = (warp - 2) / 4)
 constexpr int kBwdThreads = 320;
 struct FbSmem {
   static constexpr int TILE = 128 * kHD * 2;            // 16 KiB: a [128 x 64] bf16 operand tile
@@ -264,10 +267,10 @@ struct FbSmem {
   static constexpr int OFF_V = OFF_K + TILE;
   static constexpr int OFF_Q = OFF_V + TILE;            // 2 stages
   static constexpr int OFF_DO = OFF_Q + 2 * TILE;       // 2 stages
-  static constexpr int OFF_P = OFF_DO + 2 * TILE;       // P^T  [128 keys x 128 queries] = 2 atoms x 16 KiB
-  static constexpr int OFF_DS = OFF_P + 2 * TILE;       // dS^T
-  static constexpr int OFF_STAT = OFF_DS + 2 * TILE;    // 2 stages x (lse2[128], delta[128]) fp32
-  static constexpr int OFF_BAR = OFF_STAT + 2 * 1024;
+  static constexpr int OFF_P = OFF_DO + 2 * TILE;       // P  [128 queries x 128 keys] = 2 key atoms x 16 KiB
+  static constexpr int OFF_DS = OFF_P + 2 * TILE;       // dS
+  static constexpr int OFF_DQ = OFF_DS + 2 * TILE;      // dQ staging: 8 warps x (32 rows x 32 fp32)
+  static constexpr int OFF_BAR = OFF_DQ + 8 * 4096;
   static constexpr int BYTES = OFF_BAR + 256 + 1024;
 };
 
@@ -275,13 +278,12 @@ struct FbParams {
   int B, N, H, Npad;
   float scale, scale_log2;
   const float* lse2; const float* delta;   // [B, H, Npad]
-  float* dq_acc;                            // [B*N, H*64] fp32, zero-initialised
   __nv_bfloat16* dqkv; long long ld;        // [B*N, 3*H*64]
-  int debug_skip_dq;                        // timing experiments only (DEVIAS_DEBUG_SKIP_DQ=1): drop the dQ reduction
 };
 
 __global__ void __launch_bounds__(kBwdThreads, 1)
-flash_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO, const FbParams p) {
+flash_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
+                 const __grid_constant__ CUtensorMap tmDQ, const FbParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FbSmem::OFF_BAR);
@@ -309,6 +311,7 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
   if (warp == 0 && elect_one()) {
     prefetch_tmap(&tmQKV);
     prefetch_tmap(&tmDO);
+    prefetch_tmap(&tmDQ);
   }
   if (warp == 1) {
     if (elect_one()) {
@@ -337,23 +340,20 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
       mbar_arrive_expect_tx(kv_full, 2 * FbSmem::TILE);
       tma_load_3d(smem + FbSmem::OFF_K, &tmQKV, kv_full, D + h * kHD, k0, b);
       tma_load_3d(smem + FbSmem::OFF_V, &tmQKV, kv_full, 2 * D + h * kHD, k0, b);
-      const long long stat_row = ((long long)b * p.H + h) * p.Npad;
       for (int i = 0; i < T; ++i) {
         const int st = i & 1;
         mbar_wait(&qdo_empty[st], ((i >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(&qdo_full[st], 2 * FbSmem::TILE + 1024);
+        mbar_arrive_expect_tx(&qdo_full[st], 2 * FbSmem::TILE);
         tma_load_3d(smem + FbSmem::OFF_Q + st * FbSmem::TILE, &tmQKV, &qdo_full[st], h * kHD, i * 128, b);
         tma_load_3d(smem + FbSmem::OFF_DO + st * FbSmem::TILE, &tmDO, &qdo_full[st], h * kHD, i * 128, b);
-        bulk_load_1d(smem + FbSmem::OFF_STAT + st * 1024, p.lse2 + stat_row + i * 128, 512, &qdo_full[st]);
-        bulk_load_1d(smem + FbSmem::OFF_STAT + st * 1024 + 512, p.delta + stat_row + i * 128, 512, &qdo_full[st]);
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     if (elect_one()) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);   // [keys x queries] = K . Q^T / V . dO^T
-      constexpr uint32_t idesc_kv = umma_idesc_bf16(128, kHD, false, true);   // [keys x hd]: A = P^T/dS^T (K-major), B = dO/Q (MN-major)
-      constexpr uint32_t idesc_q = umma_idesc_bf16(128, kHD, true, true);     // [queries x hd]: A = dS^T read MN-major, B = K (MN-major)
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);   // [queries x keys] = Q K^T / dO V^T
+      constexpr uint32_t idesc_kv = umma_idesc_bf16(128, kHD, true, true);    // [keys x hd]: A = P / dS read MN-major, B = dO / Q MN-major
+      constexpr uint32_t idesc_q = umma_idesc_bf16(128, kHD, false, true);    // [queries x hd]: A = dS K-major, B = K MN-major
       const uint32_t sk = smem_u32(smem + FbSmem::OFF_K), sv = smem_u32(smem + FbSmem::OFF_V);
       const uint32_t sp = smem_u32(smem + FbSmem::OFF_P), sds = smem_u32(smem + FbSmem::OFF_DS);
       auto issue_sdp = [&](int i) {
@@ -365,9 +365,9 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         const uint64_t ddo = umma_desc_sw128(smem_u32(smem + FbSmem::OFF_DO + st * FbSmem::TILE), 0, 1024);
         const uint64_t dk_ = umma_desc_sw128(sk, 0, 1024), dv_ = umma_desc_sw128(sv, 0, 1024);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_ss(tm_s, dk_ + 2 * k, dq_ + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+        for (int k = 0; k < 4; ++k) umma_ss(tm_s, dq_ + 2 * k, dk_ + 2 * k, idesc_s, k > 0 ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_ss(tm_dp, dv_ + 2 * k, ddo + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+        for (int k = 0; k < 4; ++k) umma_ss(tm_dp, ddo + 2 * k, dv_ + 2 * k, idesc_s, k > 0 ? 1u : 0u);
         umma_commit(sdp_full);
       };
       mbar_wait(kv_full, 0);
@@ -377,27 +377,25 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         const int st = i & 1;
         mbar_wait(pds_full, i & 1);
         tc_fence_after();
+        // P / dS tiles: [128 query rows][2 key atoms of 64]; read MN-major: M = keys (atoms 16 KiB apart), K = query rows
+        const uint64_t ap_mn = umma_desc_sw128(sp, FbSmem::TILE, 1024), ads_mn = umma_desc_sw128(sds, FbSmem::TILE, 1024);
         // B operands, MN-major over the 128 query rows of this stage (one 64-wide atom, 16 rows per UMMA_K)
         const uint64_t bdo = umma_desc_sw128(smem_u32(smem + FbSmem::OFF_DO + st * FbSmem::TILE), 128 * 128, 1024);
         const uint64_t bq = umma_desc_sw128(smem_u32(smem + FbSmem::OFF_Q + st * FbSmem::TILE), 128 * 128, 1024);
-        const uint64_t ap = umma_desc_sw128(sp, 0, 1024), ads = umma_desc_sw128(sds, 0, 1024);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {   // K = 128 queries: k-steps 0..3 in atom 0, 4..7 in atom 1 (+16 KiB)
-          const uint64_t aoff = (uint64_t)((k >> 2) * (FbSmem::TILE >> 4) + (k & 3) * 2);
-          umma_ss(tm_dv, ap + aoff, bdo + 128 * k, idesc_kv, (i > 0 || k > 0) ? 1u : 0u);
-        }
+        for (int k = 0; k < 8; ++k) umma_ss(tm_dv, ap_mn + 128 * k, bdo + 128 * k, idesc_kv, (i > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) umma_ss(tm_dk, ads_mn + 128 * k, bq + 128 * k, idesc_kv, (i > 0 || k > 0) ? 1u : 0u);
+        // dQ_i[q, hd] = sum_keys dS[q, key] K[key, hd]: A = dS K-major (keys: 2 atoms x 4 k-steps), B = K MN-major
+        mbar_wait(&dq_empty[i & 1], ((i >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint64_t ads = umma_desc_sw128(sds, 0, 1024);
+        const uint64_t bk = umma_desc_sw128(sk, 128 * 128, 1024);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const uint64_t aoff = (uint64_t)((k >> 2) * (FbSmem::TILE >> 4) + (k & 3) * 2);
-          umma_ss(tm_dk, ads + aoff, bq + 128 * k, idesc_kv, (i > 0 || k > 0) ? 1u : 0u);
+          umma_ss(tm_dq[i & 1], ads + aoff, bk + 128 * k, idesc_q, k > 0 ? 1u : 0u);
         }
-        // dQ_i[q, hd] = sum_keys dS[q, key] K[key, hd]: A = dS^T tile read MN-major (M = q: atoms 16 KiB apart), K = keys
-        mbar_wait(&dq_empty[i & 1], ((i >> 1) & 1) ^ 1);
-        tc_fence_after();
-        const uint64_t ads_mn = umma_desc_sw128(sds, FbSmem::TILE, 1024);
-        const uint64_t bk = umma_desc_sw128(sk, 128 * 128, 1024);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) umma_ss(tm_dq[i & 1], ads_mn + 128 * k, bk + 128 * k, idesc_q, k > 0 ? 1u : 0u);
         umma_commit(&dq_full[i & 1]);
         umma_commit(pds_empty);
         umma_commit(&qdo_empty[st]);
@@ -407,14 +405,19 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
     __syncwarp();
   } else {
     const int cw = warp - 2;                 // 0..7
-    const int q4 = warp & 3;                 // TMEM lane quarter
-    const int g = cw >> 2;                   // column half
+    const int q4 = warp & 3;                 // TMEM lane quarter = query-row quarter
+    const int g = cw >> 2;                   // key-column half
     const int lane = (int)lane_id();
-    const int r = q4 * 32 + lane;            // key row (S^T/dP^T) or query row (dQ) inside the tile
+    const int r = q4 * 32 + lane;            // query row inside the tile (S/dP/dQ) or key row (epilogue)
     const uint32_t lane_sel = (uint32_t)(q4 * 32) << 16;
     const uint32_t prow = smem_u32(smem + FbSmem::OFF_P + g * FbSmem::TILE + r * 128);
     const uint32_t dsrow = smem_u32(smem + FbSmem::OFF_DS + g * FbSmem::TILE + r * 128);
+    uint8_t* dq_box_p = smem + FbSmem::OFF_DQ + cw * 4096;
+    const uint32_t dq_box = smem_u32(dq_box_p);
+    const long long stat_row = ((long long)b * p.H + h) * p.Npad;
+    const uint64_t cc = f2_pack(p.scale_log2, p.scale_log2);
     auto reduce_dq = [&](int i) {
+      // dQ_i rows of this warp, columns [32 g, 32 g + 32): TMEM -> swizzled smem box -> TMA reduce-add (fp32, at L2)
       mbar_wait(&dq_full[i & 1], (i >> 1) & 1);
       tc_fence_after();
       uint32_t t[32];
@@ -422,24 +425,28 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&dq_empty[i & 1]);
-      const int qi = i * 128 + r;
-      if (qi < p.N && !p.debug_skip_dq) {
-        float* dst = p.dq_acc + ((long long)b * p.N + qi) * D + h * kHD + 32 * g;
+      if (lane == 0) {
+        mbar_arrive(&dq_empty[i & 1]);
+        bulk_wait_read0();                   // previous reduce has finished reading the box
+      }
+      __syncwarp();
 #pragma unroll
-        for (int c = 0; c < 8; ++c)
-          red_add_v4_f32(dst + 4 * c, __uint_as_float(t[4 * c]), __uint_as_float(t[4 * c + 1]), __uint_as_float(t[4 * c + 2]),
-                         __uint_as_float(t[4 * c + 3]));
+      for (int c = 0; c < 8; ++c) sts128(dq_box + lane * 128 + ((c ^ (lane & 7)) << 4), t[4 * c], t[4 * c + 1], t[4 * c + 2], t[4 * c + 3]);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        tma_reduce_add_3d(&tmDQ, dq_box_p, h * kHD + 32 * g, i * 128 + q4 * 32, b);
+        bulk_commit();
       }
     };
     for (int i = 0; i < T; ++i) {
-      const int st = i & 1;
-      const uint32_t lse_s = smem_u32(smem + FbSmem::OFF_STAT + st * 1024) + 256 * g;   // lse2[64 g ..]
-      const uint32_t del_s = lse_s + 512;
-      mbar_wait(&qdo_full[st], (i >> 1) & 1);      // lse2 / delta of this query tile have landed
+      const int qi = i * 128 + r;
+      const float lse = __ldg(p.lse2 + stat_row + qi);        // padded rows: +inf -> P = 0
+      const float del = __ldg(p.delta + stat_row + qi);       // padded rows: 0
+      const uint64_t nl = f2_pack(-lse, -lse), nd = f2_pack(-del, -del);
       mbar_wait(sdp_full, i & 1);
       tc_fence_after();
-      uint32_t pp[32], dd[32];                     // packed bf16x2: P^T and dS^T for this thread's 64 queries
+      uint32_t pp[32], dd[32];                     // packed bf16x2: P and dS for this thread's 64 keys
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint32_t sv_[32], dp_[32];
@@ -448,18 +455,18 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         tmem_ld_wait();
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-          const float2 ls = lds64(lse_s + 4 * (32 * c + 2 * k));
-          const float2 dl = lds64(del_s + 4 * (32 * c + 2 * k));
-          const float p0 = fast_exp2(fmaf(__uint_as_float(sv_[2 * k]), p.scale_log2, -ls.x));
-          const float p1 = fast_exp2(fmaf(__uint_as_float(sv_[2 * k + 1]), p.scale_log2, -ls.y));
+          const uint64_t x = f2_fma(f2_pack(__uint_as_float(sv_[2 * k]), __uint_as_float(sv_[2 * k + 1])), cc, nl);
+          const float p0 = fast_exp2(f2_lo(x)), p1 = fast_exp2(f2_hi(x));
+          const uint64_t pv = f2_pack(p0, p1);
+          const uint64_t ds = f2_mul(pv, f2_add(f2_pack(__uint_as_float(dp_[2 * k]), __uint_as_float(dp_[2 * k + 1])), nd));
           pp[16 * c + k] = pack_bf16(p0, p1);
-          dd[16 * c + k] = pack_bf16(p0 * (__uint_as_float(dp_[2 * k]) - dl.x), p1 * (__uint_as_float(dp_[2 * k + 1]) - dl.y));
+          dd[16 * c + k] = pack_bf16(f2_lo(ds), f2_hi(ds));
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(sdp_empty);
-      mbar_wait(pds_empty, (i & 1) ^ 1);           // the MMAs of tile i-1 have finished reading P^T / dS^T
+      mbar_wait(pds_empty, (i & 1) ^ 1);           // the MMAs of tile i-1 have finished reading P / dS
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         const int off = (c ^ (r & 7)) << 4;
@@ -472,7 +479,7 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
       if (i > 0) reduce_dq(i - 1);
     }
     reduce_dq(T - 1);
-    // epilogue: dK (scaled) and dV rows of this key tile
+    // epilogue: dK (scaled) and dV rows of this key tile (thread = key row)
     mbar_wait(acc_full, 0);
     tc_fence_after();
     const int ki = k0 + r;
@@ -499,6 +506,8 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
                                   pack_bf16(sc * __uint_as_float(t1[8 * c + 6]), sc * __uint_as_float(t1[8 * c + 7])));
       }
     }
+    if (lane == 0) bulk_wait0();
+    __syncwarp();
   }
   tc_fence_before();
   __syncthreads();
@@ -596,11 +605,18 @@ extern "C" int devias_flash_attn_bwd(const void* qkv, const void* out, const voi
   const int D = heads * kHD;
   const int Npad = (seq + 127) / 128 * 128;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  CUtensorMap tmQKV, tmDO;
+  CUtensorMap tmQKV, tmDO, tmDQ;
   int rc = make_qkv_tmap(&tmQKV, qkv, batch, seq, 3 * D, 128);
   if (rc) return rc;
   rc = make_qkv_tmap(&tmDO, dout, batch, seq, D, 128);
   if (rc) return rc;
+  {  // fp32 dQ accumulator [B, N, H*64]: boxes of 32 floats x 32 rows; rows past N are clipped by the TMA unit
+    const uint64_t dims[3] = {(uint64_t)D, (uint64_t)seq, (uint64_t)batch};
+    const uint64_t str[2] = {(uint64_t)D * 4, (uint64_t)seq * D * 4};
+    const uint32_t box[3] = {32, 32, 1};
+    rc = make_tmap_nd(&tmDQ, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, dq_ws, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
   static bool attr_done = false;
   if (!attr_done) {
     DV_CHECK_CUDA(cudaFuncSetAttribute(flash_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FbSmem::BYTES));
@@ -613,11 +629,11 @@ extern "C" int devias_flash_attn_bwd(const void* qkv, const void* out, const voi
                                                                   static_cast<const __nv_bfloat16*>(dout), delta_ws, batch, seq,
                                                                   heads, Npad);
   }
-  FbParams p{batch, seq, heads, Npad, scale, scale * 1.4426950408889634f, lse2, delta_ws, dq_ws,
-             static_cast<__nv_bfloat16*>(dqkv), (long long)3 * D, getenv("DEVIAS_DEBUG_SKIP_DQ") != nullptr ? 1 : 0};
+  FbParams p{batch, seq, heads, Npad, scale, scale * 1.4426950408889634f, lse2, delta_ws,
+             static_cast<__nv_bfloat16*>(dqkv), (long long)3 * D};
   const int k_tiles = (seq + 127) / 128;
   const int prof = prof_begin(DEVIAS_PROF_ATTN, 10.0 * batch * heads * (double)seq * seq * kHD, s);
-  flash_bwd_kernel<<<batch * heads * k_tiles, kBwdThreads, FbSmem::BYTES, s>>>(tmQKV, tmDO, p);
+  flash_bwd_kernel<<<batch * heads * k_tiles, kBwdThreads, FbSmem::BYTES, s>>>(tmQKV, tmDO, tmDQ, p);
   prof_end(prof, s);
   {
     const long long n8 = (long long)batch * seq * (D / 8);
