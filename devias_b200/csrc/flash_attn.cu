@@ -54,7 +54,7 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint64_t* s_empty = bars + 9;            // 2
   uint64_t* p_full = bars + 11;            // 2
   uint64_t* p_empty = bars + 13;           // 2
-  uint64_t* pv_done = bars + 15;           // 1: completes once per key tile, after P_j V_j has been accumulated into O
+  uint64_t* pv_done = bars + 15;           // 4-deep ring: pv_done[j % 4] completes when P_j V_j has been accumulated into O
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
 
   const int warp = threadIdx.x >> 5;
@@ -78,7 +78,7 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4);
         mbar_init(&p_full[i], 4); mbar_init(&p_empty[i], 1);
       }
-      mbar_init(pv_done, 1);
+      for (int i = 0; i < 4; ++i) mbar_init(&pv_done[i], 1);
       fence_barrier_init();
     }
     __syncwarp();
@@ -131,9 +131,8 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const uint64_t db = umma_desc_sw128(smem_u32(smem + FaSmem::OFF_V + st * FaSmem::V_BYTES), kKT * 128, 1024);
 #pragma unroll
         for (int k = 0; k < kKT / 16; ++k) umma_ss(tm_o, da + 2 * k, db + 128 * k, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
-        umma_commit(pv_done);
+        umma_commit(&pv_done[j & 3]);
         umma_commit(&kv_empty[st]);
-        umma_commit(&p_empty[j & 1]);
       }
     }
     __syncwarp();
@@ -165,16 +164,17 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           if (i + 32 >= valid) s1[i] = 0xff800000u;
         }
       }
-      float mx = -INFINITY;
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // four independent chains (latency, not throughput, matters)
 #pragma unroll
-      for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(s0[i]), __uint_as_float(s1[i])));
+      for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], fmaxf(__uint_as_float(s0[i]), __uint_as_float(s1[i])));
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       const float m_run = fmaxf(m, mx * p.scale_log2);   // scale > 0: max(c s) = c max(s)
-      // observe EVERY phase of pv_done in order (a parity wait can only tell the current phase from the previous one);
-      // by now P_{j-1} V_{j-1}, issued right after the previous iteration, has normally retired already
-      if (j > 0) mbar_wait(pv_done, (j - 1) & 1);
       if (__any_sync(0xffffffffu, m_run > m + 8.0f)) {
         const float alpha = fast_exp2(m - m_run);       // 0 on the first tile (m = -inf)
         if (j > 0) {
+          // P_{j-1} V_{j-1} must have landed in O.  pv_done is a 4-deep ring, so its parity cannot alias: the MMA warp is
+          // never more than one tile ahead of this warp (it needs our p_full arrival for tile j).
+          mbar_wait(&pv_done[(j - 1) & 3], ((j - 1) >> 2) & 1);
           tc_fence_after();
 #pragma unroll
           for (int hlf = 0; hlf < 2; ++hlf) {
@@ -192,9 +192,10 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       }
       const uint64_t negm = f2_pack(-m, -m);
       // P_j -> smem (K-major, 128B swizzle: 16-byte chunk c of row r lands at chunk c ^ (r & 7))
-      mbar_wait(&p_empty[j & 1], ((j >> 1) & 1) ^ 1);     // (implied by pv_done(j-1); kept as the explicit buffer hand-off)
+      // P buffer (j & 1) is free: S_j was issued after P_{j-2} V_{j-2} and the tensor pipe retires in order, so the
+      // s_full wait above already implies it.
       const uint32_t prow = p_row_base + (j & 1) * FaSmem::P_BYTES;
-      uint64_t sum2 = 0ull;
+      uint64_t sum2[4] = {0ull, 0ull, 0ull, 0ull};
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         uint32_t pk[4];
@@ -205,12 +206,13 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                                    : f2_pack(__uint_as_float(s1[e]), __uint_as_float(s1[e + 1]));
           const uint64_t y = f2_fma(x, cc, negm);
           const float e0 = fast_exp2(f2_lo(y)), e1 = fast_exp2(f2_hi(y));
-          sum2 = f2_add(sum2, f2_pack(e0, e1));
+          sum2[i] = f2_add(sum2[i], f2_pack(e0, e1));
           pk[i] = pack_bf16(e0, e1);
         }
         sts128(prow + ((c ^ (r & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
       }
-      l += f2_lo(sum2) + f2_hi(sum2);
+      const uint64_t st = f2_add(f2_add(sum2[0], sum2[1]), f2_add(sum2[2], sum2[3]));
+      l += f2_lo(st) + f2_hi(st);
       fence_proxy_async();
       tc_fence_before();
       __syncwarp();
@@ -218,7 +220,7 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     }
     float o[kHD];
     {
-      mbar_wait(pv_done, (T - 1) & 1);
+      mbar_wait(&pv_done[(T - 1) & 3], ((T - 1) >> 2) & 1);
       tc_fence_after();
       const float inv = 1.0f / l;
 #pragma unroll
@@ -418,7 +420,6 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
     const uint64_t cc = f2_pack(p.scale_log2, p.scale_log2);
     auto reduce_dq = [&](int i) {
       // dQ_i rows of this warp, columns [32 g, 32 g + 32): TMEM -> swizzled smem box -> TMA reduce-add (fp32, at L2)
-      mbar_wait(&dq_full[i & 1], (i >> 1) & 1);
       tc_fence_after();
       uint32_t t[32];
       tmem_ld_32x32b_x32(tm_dq[i & 1] + lane_sel + 32 * g, t);
@@ -466,7 +467,8 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(sdp_empty);
-      mbar_wait(pds_empty, (i & 1) ^ 1);           // the MMAs of tile i-1 have finished reading P / dS
+      // dQ_{i-1} is the last MMA of tile i-1: once it has retired, P / dS of tile i-1 have been consumed as well
+      if (i > 0) mbar_wait(&dq_full[(i - 1) & 1], ((i - 1) >> 1) & 1);
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         const int off = (c ^ (r & 7)) << 4;
@@ -478,6 +480,7 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
       if (lane == 0) mbar_arrive(pds_full);
       if (i > 0) reduce_dq(i - 1);
     }
+    mbar_wait(&dq_full[(T - 1) & 1], ((T - 1) >> 1) & 1);
     reduce_dq(T - 1);
     // epilogue: dK (scaled) and dV rows of this key tile (thread = key row)
     mbar_wait(acc_full, 0);

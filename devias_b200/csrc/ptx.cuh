@@ -51,20 +51,31 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded spin: a protocol bug traps (-> cudaErrorLaunchFailure at the next sync) instead of hanging the GPU box.
-#ifndef DV_SPIN_LIMIT
-#define DV_SPIN_LIMIT (1u << 28)
-#endif
+// Release builds spin on try_wait (which itself suspends the thread for a hardware-defined time slice); -DDV_DEBUG_SPIN
+// bounds the spin so that a protocol bug traps (-> cudaErrorLaunchFailure at the next sync) instead of hanging the GPU box.
+#ifdef DV_DEBUG_SPIN
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > DV_SPIN_LIMIT) {
-      printf("devias_b200: mbarrier timeout block %d thread %d bar %u parity %u\n", blockIdx.x, threadIdx.x,
-             smem_u32(bar), parity);
+    if (++spins > (1u << 26)) {
+      printf("devias_b200: mbarrier timeout block %d thread %d bar %u parity %u\n", blockIdx.x, threadIdx.x, smem_u32(bar), parity);
       __trap();
     }
   }
 }
+#else
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%0], %1;\n\t"
+      "@P bra.uni WAIT_DONE;\n\t"
+      "bra.uni WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+#endif
 
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
@@ -263,11 +274,21 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
 }
 
 // ---------------------------------------------------------------- packed fp32x2 math (FFMA2 / FADD2 / FMUL2 on sm_100)
-__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
-  return static_cast<uint64_t>(__float_as_uint(lo)) | (static_cast<uint64_t>(__float_as_uint(hi)) << 32);
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {   // register-pair rename, no ALU work when lo/hi are adjacent
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
 }
-__device__ __forceinline__ float f2_lo(uint64_t v) { return __uint_as_float(static_cast<uint32_t>(v)); }
-__device__ __forceinline__ float f2_hi(uint64_t v) { return __uint_as_float(static_cast<uint32_t>(v >> 32)); }
+__device__ __forceinline__ float f2_lo(uint64_t v) {
+  float lo, hi;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+  return lo;
+}
+__device__ __forceinline__ float f2_hi(uint64_t v) {
+  float lo, hi;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+  return hi;
+}
 __device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
   uint64_t r;
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
