@@ -221,7 +221,7 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------------------------------------------------------- warm-up (+ graph capture of the whole step)
-    use_graph = not args.no_graph and world == 1
+    use_graph = not args.no_graph
     for i in range(max(args.warmup, 3)):
         step(devb[i % nbuf])
     barrier()
@@ -326,7 +326,8 @@ def main():
                                    f'(fwd + TrainLoss + bwd + fused AdamW), drop_path {cfg["drop_path_rate"]}',
                        'clips_per_gpu': B, 'global_batch': B * world, 'parallelism': f'dp{world}',
                        'l2': 'per-step working set (activations + weights, several GB) far exceeds the 126 MB L2; no flush needed',
-                       'loss': loss_val, 'launch_mode': 'cuda-graph replay of the whole step' if graphed is not None else 'eager'},
+                       'loss': loss_val, 'launch_mode': ('eager' if graphed is None else 'cuda-graph replay of the whole step' if world == 1 else
+                                       'cuda graph (fwd+bwd) -> NCCL all-reduce of flat fp32 gradient buckets -> cuda graph (AdamW)')},
             'clocks': clk,
             'gpu_launches': int(launches),
             'roofline': {'kernel': 'gemm_bf16_kernel (tcgen05/TMEM/TMA)', 'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf,

@@ -97,6 +97,18 @@ class GradReducer:
             for flat in self.buckets:
                 flat.mul_(inv)
 
+    def allreduce_all(self):
+        """un-overlapped exchange of every bucket (used between the two CUDA graphs of a graphed step, where the
+        per-parameter hooks do not run): all buckets are enqueued back to back, then awaited and averaged"""
+        if self.world <= 1:
+            return
+        works = [dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.pg, async_op=True) for flat in self.buckets]
+        for w in works:
+            w.wait()
+        inv = 1.0 / self.world
+        for flat in self.buckets:
+            flat.mul_(inv)
+
     def remove(self):
         for h in self._hooks:
             h.remove()

@@ -62,13 +62,22 @@ class GraphedTrainStep:
     def __init__(self, model, train_criterion, optimizer, batches, reducer=None, warmup=3):
         self.model, self.crit, self.opt, self.reducer = model, train_criterion, optimizer, reducer
         self.batches = list(batches)
+        # With a reducer the step is split into two graphs around an eager NCCL exchange of the flat gradient buckets:
+        #   graph A: forward + loss + backward (gradients accumulate straight into the buckets; hooks are python and do not
+        #            run on replay, so the per-bucket overlap is traded for ~2000 fewer launches per step)
+        #   eager  : all-reduce of the buckets (NCCL over NVLink), 1/world
+        #   graph B: optimizer update + bucket memsets
+        self.split = reducer is not None
+        if self.split:
+            reducer.enabled = False
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
         side.wait_stream(cur)
         with torch.cuda.stream(side):                      # warm-up off the capture stream (allocator, lazy inits)
             for i in range(warmup):
-                self._body(self.batches[i % len(self.batches)])
-                self._zero()
+                self._fwd_bwd(self.batches[i % len(self.batches)])
+                self._exchange()
+                self._update()
         cur.wait_stream(side)
         torch.cuda.synchronize()
         self.graphs, self.losses = [], []
@@ -78,29 +87,42 @@ class GraphedTrainStep:
             g = torch.cuda.CUDAGraph()
             n0 = _lib.launch_count()
             with torch.cuda.graph(g, pool=pool):
-                loss = self._body(b)
+                loss = self._fwd_bwd(b)
+                if not self.split:
+                    self.opt.step()
             self.launches_per_step = _lib.launch_count() - n0
             pool = g.pool()
             self.graphs.append(g)
             self.losses.append(loss)
-            self._zero()
+            if not self.split:
+                self.opt.zero_grad(set_to_none=True)
+        self.update_graph = None
+        if self.split:
+            self.update_graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.update_graph, pool=pool):
+                self._update()
 
-    def _zero(self):
-        if self.reducer is not None:
+    def _fwd_bwd(self, b):
+        loss, _, _ = train_class_batch(self.model, None, b['clip'], b['target'], self.crit, (b['fg'], b['fgf']),
+                                       teacher_logits=b['teacher'])
+        loss.backward()
+        return loss.detach()
+
+    def _exchange(self):
+        if self.split:
+            self.reducer.allreduce_all()
+
+    def _update(self):
+        self.opt.step()
+        if self.split:
             self.reducer.zero_grad()
         else:
             self.opt.zero_grad(set_to_none=True)
 
-    def _body(self, b):
-        loss, _, _ = train_class_batch(self.model, None, b['clip'], b['target'], self.crit, (b['fg'], b['fgf']),
-                                       teacher_logits=b['teacher'])
-        loss.backward()
-        if self.reducer is not None:
-            self.reducer.finish()
-        self.opt.step()
-        return loss.detach()
-
     def __call__(self, index=0):
         """replay the step on static batch `index`; returns the (static) loss tensor of that graph"""
         self.graphs[index].replay()
+        if self.split:
+            self.reducer.allreduce_all()
+            self.update_graph.replay()
         return self.losses[index]
