@@ -64,25 +64,25 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
 }
 
 // Backward.  dy: gradient w.r.t. the LN output (bf16 or fp32).  d_resid (optional, fp32) is added to the result
-// (the skip connection); dx may alias d_resid.  Column reductions are accumulated per warp in registers over a
-// grid-stride loop, combined through shared memory and flushed with one red.add per column per block.
+// (the skip connection); dx may alias d_resid.  The three column reductions (dgamma, dbeta, colsum(dx)) are kept in
+// per-warp shared-memory rows instead of registers (which held occupancy to one block per SM and the kernel to ~40 % of
+// HBM bandwidth); they are combined across the block's warps at the end and flushed with one atomicAdd per column.
 template <int D, bool DY_BF16>
-__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x,
-                                                            const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                            const float* __restrict__ gamma, const float* d_resid,
-                                                            float* dx, __nv_bfloat16* __restrict__ dx_bf16,
-                                                            float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                            float* __restrict__ dx_colsum, int M) {
+__global__ void __launch_bounds__(256, 3) layernorm_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x,
+                                                               const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                               const float* __restrict__ gamma, const float* d_resid,
+                                                               float* dx, __nv_bfloat16* __restrict__ dx_bf16,
+                                                               float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                               float* __restrict__ dx_colsum, int M) {
   constexpr int V = RowRegs<D>::V;
+  extern __shared__ float4 ln_acc[];                 // [3][8 warps][D/4]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  float4 g[V];
-  float4 acc_g[V], acc_b[V], acc_c[V];
-  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  float4* accg = ln_acc + (0 * 8 + warp) * (D / 4);
+  float4* accb = ln_acc + (1 * 8 + warp) * (D / 4);
+  float4* accc = ln_acc + (2 * 8 + warp) * (D / 4);
 #pragma unroll
-  for (int i = 0; i < V; ++i) {
-    g[i] = __ldg(g4 + lane + 32 * i);
-    acc_g[i] = acc_b[i] = acc_c[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
+  for (int i = 0; i < V; ++i) accg[lane + 32 * i] = accb[lane + 32 * i] = accc[lane + 32 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
   for (int row = blockIdx.x * nwarp + warp; row < M; row += gridDim.x * nwarp) {
     const float mu = __ldg(mean + row), r = __ldg(rstd + row);
     const float4* xr = reinterpret_cast<const float4*>(x + (long long)row * D);
@@ -99,10 +99,17 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void* __restri
       } else {
         d[i] = __ldcs(reinterpret_cast<const float4*>(static_cast<const float*>(dy) + (long long)row * D) + lane + 32 * i);
       }
-      acc_b[i].x += d[i].x; acc_b[i].y += d[i].y; acc_b[i].z += d[i].z; acc_b[i].w += d[i].w;
-      acc_g[i].x = fmaf(d[i].x, xh[i].x, acc_g[i].x); acc_g[i].y = fmaf(d[i].y, xh[i].y, acc_g[i].y);
-      acc_g[i].z = fmaf(d[i].z, xh[i].z, acc_g[i].z); acc_g[i].w = fmaf(d[i].w, xh[i].w, acc_g[i].w);
-      d[i].x *= g[i].x; d[i].y *= g[i].y; d[i].z *= g[i].z; d[i].w *= g[i].w;  // dy * gamma
+    }
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      float4 ab = accb[lane + 32 * i], ag = accg[lane + 32 * i];
+      ab.x += d[i].x; ab.y += d[i].y; ab.z += d[i].z; ab.w += d[i].w;
+      ag.x = fmaf(d[i].x, xh[i].x, ag.x); ag.y = fmaf(d[i].y, xh[i].y, ag.y);
+      ag.z = fmaf(d[i].z, xh[i].z, ag.z); ag.w = fmaf(d[i].w, xh[i].w, ag.w);
+      accb[lane + 32 * i] = ab;
+      accg[lane + 32 * i] = ag;
+      const float4 g = __ldg(g4 + lane + 32 * i);
+      d[i].x *= g.x; d[i].y *= g.y; d[i].z *= g.z; d[i].w *= g.w;  // dy * gamma
       s1 += (d[i].x + d[i].y) + (d[i].z + d[i].w);
       s2 += (d[i].x * xh[i].x + d[i].y * xh[i].y) + (d[i].z * xh[i].z + d[i].w * xh[i].w);
     }
@@ -125,26 +132,26 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void* __restri
       if (dx != nullptr) reinterpret_cast<float4*>(dx + (long long)row * D)[lane + 32 * i] = o;
       if (dx_bf16 != nullptr)
         reinterpret_cast<uint2*>(dx_bf16 + (long long)row * D)[lane + 32 * i] = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
-      acc_c[i].x += o.x; acc_c[i].y += o.y; acc_c[i].z += o.z; acc_c[i].w += o.w;
+      if (dx_colsum != nullptr) {
+        float4 ac = accc[lane + 32 * i];
+        ac.x += o.x; ac.y += o.y; ac.z += o.z; ac.w += o.w;
+        accc[lane + 32 * i] = ac;
+      }
     }
   }
-  // block-level combine: smem [nwarp][D] per quantity, done one quantity at a time to bound shared memory
-  __shared__ float red[8][D];
-  auto flush = [&](const float4 (&acc)[V], float* __restrict__ gout) {
+  __syncthreads();
+  const float* accf = reinterpret_cast<const float*>(ln_acc);
+  auto flush = [&](int which, float* __restrict__ gout) {
     if (gout == nullptr) return;  // uniform across the block
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < V; ++i) reinterpret_cast<float4*>(red[warp])[lane + 32 * i] = acc[i];
-    __syncthreads();
     for (int c = threadIdx.x; c < D; c += blockDim.x) {
       float s = 0.f;
-      for (int w = 0; w < nwarp; ++w) s += red[w][c];
+      for (int w = 0; w < nwarp; ++w) s += accf[(which * 8 + w) * D + c];
       atomicAdd(gout + c, s);
     }
   };
-  flush(acc_g, dgamma);
-  flush(acc_b, dbeta);
-  flush(acc_c, dx_colsum);
+  flush(0, dgamma);
+  flush(1, dbeta);
+  flush(2, dx_colsum);
 }
 
 // column sums of a bf16 [M,N] matrix into fp32 [N] (bias gradients of qkv / fc1): out[n] += sum_m a[m,n]
@@ -203,14 +210,21 @@ extern "C" int devias_layernorm_bwd(const void* dy, int dy_is_bf16, const float*
   DV_REQUIRE(dim == 768, "only dim = 768 is instantiated");
   if (rows <= 0) return DEVIAS_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  int grid = sm_count() * 4;
+  int grid = sm_count() * 3;
   const int need = (rows + 7) / 8;
   if (grid > need) grid = need;
+  constexpr int kLnSmem = 3 * 8 * 768 * 4;   // 72 KiB: three per-warp accumulator rows
+  static bool attr_done = false;
+  if (!attr_done) {
+    DV_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<768, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLnSmem));
+    DV_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<768, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLnSmem));
+    attr_done = true;
+  }
   if (dy_is_bf16)
-    layernorm_bwd_kernel<768, true><<<grid, 256, 0, s>>>(dy, x, mean, rstd, gamma, d_resid, dx,
+    layernorm_bwd_kernel<768, true><<<grid, 256, kLnSmem, s>>>(dy, x, mean, rstd, gamma, d_resid, dx,
                                                          static_cast<__nv_bfloat16*>(dx_bf16), dgamma, dbeta, dx_colsum, rows);
   else
-    layernorm_bwd_kernel<768, false><<<grid, 256, 0, s>>>(dy, x, mean, rstd, gamma, d_resid, dx,
+    layernorm_bwd_kernel<768, false><<<grid, 256, kLnSmem, s>>>(dy, x, mean, rstd, gamma, d_resid, dx,
                                                           static_cast<__nv_bfloat16*>(dx_bf16), dgamma, dbeta, dx_colsum, rows);
   DV_CHECK_CUDA(cudaGetLastError());
   count_launch();
