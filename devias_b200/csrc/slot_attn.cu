@@ -236,6 +236,248 @@ slot_stream_fwd_kernel(const __grid_constant__ CUtensorMap tmTok, const SlotPara
 }
 
 // =====================================================================================================================
+// Forward, version 2 (HS = 8, 16): warp-specialised and software-pipelined so that the two FMA phases of consecutive tiles
+// overlap instead of alternating behind block-wide barriers (ncu on v1: 40 % of warp samples stalled at __syncthreads,
+// 37 % issue utilisation, 25 % of HBM peak), and packed FFMA2 / FADD2 halve the issue slots per token.
+//   group A (warps 0-3): phase 1 of tile t+1 (dots + moments, lane <-> token) and phase 1b (thread <-> (token, slot):
+//                        statistics, logits, slot-axis softmax by warp shuffles, weights) -> w ring (2 deep)
+//   group B (warps 4-7): phase 2 of tile t (thread <-> 3 channel pairs, weights broadcast from the w ring)
+//   one thread of group A is the TMA producer; tile stages are released by both groups through an mbarrier.
+template <int HS>
+struct SlotCfg2 {
+  static constexpr int STAGES = (HS <= 8) ? 4 : 3;
+  static constexpr int OFF_TILE = 0;
+  static constexpr int OFF_G = STAGES * kSTileBytes;                 // g[HS][768] fp32
+  static constexpr int PART_STRIDE = HS + 4;                         // dots[HS], s1, s2, x0, pad
+  static constexpr int OFF_PART = OFF_G + HS * kSD * 4;              // partial[4 warps][16 tokens][PART_STRIDE]
+  static constexpr int OFF_W = OFF_PART + 4 * kST * PART_STRIDE * 4; // w ring [2][16 tokens][HS] pairs (w, w)
+  static constexpr int OFF_BAR = OFF_W + 2 * kST * HS * 8;
+  static constexpr int BYTES = OFF_BAR + 128 + 1024;
+};
+
+template <int HS>
+__global__ void __launch_bounds__(kSlotThreads, 1)
+slot_stream_fwd2_kernel(const __grid_constant__ CUtensorMap tmTok, const SlotParams p) {
+  using Cfg = SlotCfg2<HS>;
+  constexpr int S = HS / 4;
+  constexpr int TPW = 32 / S;                 // tokens per warp-unit in phase 1b
+  constexpr int UNITS = 4 * (kST / TPW);      // (head, token group) units per tile
+  constexpr int UPW = UNITS / 4;              // units per group-A warp
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* g_s = reinterpret_cast<float*>(smem + Cfg::OFF_G);
+  float* part = reinterpret_cast<float*>(smem + Cfg::OFF_PART);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+  uint64_t* full = bars;                       // STAGES
+  uint64_t* tile_empty = bars + Cfg::STAGES;   // STAGES (8 warp arrivals)
+  uint64_t* w_full = tile_empty + Cfg::STAGES; // 2 (4 arrivals)
+  uint64_t* w_empty = w_full + 2;              // 2 (4 arrivals)
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.y;
+  const int tile0 = blockIdx.x * p.tiles_per_cta;
+  const int ntiles = min(p.tiles_per_cta, p.tiles_per_clip - tile0);
+  if (ntiles <= 0) return;
+
+  if (tid == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&tile_empty[s], 8); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&w_full[s], 4); mbar_init(&w_empty[s], 4); }
+    fence_barrier_init();
+  }
+  {
+    const float4* src = reinterpret_cast<const float4*>(p.g + (long long)b * HS * kSD);
+    float4* dst = reinterpret_cast<float4*>(g_s);
+    for (int i = tid; i < HS * kSD / 4; i += kSlotThreads) dst[i] = __ldg(src + i);
+  }
+  __syncthreads();
+
+  const uint32_t g_u = smem_u32(g_s), part_u = smem_u32(part), w_u = smem_u32(smem + Cfg::OFF_W);
+  auto issue = [&](int it) {   // one thread: 24 boxes of 32 floats x 16 tokens
+    const int st = it % Cfg::STAGES;
+    mbar_wait(&tile_empty[st], ((it / Cfg::STAGES) & 1) ^ 1);
+    mbar_arrive_expect_tx(&full[st], kSTileBytes);
+    uint8_t* dst = smem + Cfg::OFF_TILE + st * kSTileBytes;
+    const int tok0 = (tile0 + it) * kST;
+#pragma unroll 1
+    for (int bx = 0; bx < kSBoxes; ++bx) tma_load_3d(dst + bx * (kST * 128), &tmTok, &full[st], bx * 32, tok0, b);
+  };
+  constexpr int PRE = Cfg::STAGES - 2;         // tiles in flight ahead of group A
+
+  if (warp < 4) {
+    // =============================================================== group A
+    if (tid == 0) {
+      for (int it = 0; it < PRE && it < ntiles; ++it) issue(it);
+    }
+    const int tok_l = lane & 15, half = lane >> 4;
+    const int c_base = warp * 48 + half;                       // this lane's 24 chunks: every other chunk of the warp's 192 channels
+                                                               // (the two half-warps then read ADJACENT g chunks: no bank conflict)
+    float accA[UPW], accM[UPW];
+#pragma unroll
+    for (int k = 0; k < UPW; ++k) { accA[k] = 0.f; accM[k] = 0.f; }
+    for (int it = 0; it < ntiles; ++it) {
+      const int st = it % Cfg::STAGES;
+      if (tid == 0 && it + PRE < ntiles) issue(it + PRE);
+      mbar_wait(&full[st], (it / Cfg::STAGES) & 1);
+      const uint32_t tile = smem_u32(smem + Cfg::OFF_TILE + st * kSTileBytes);
+      const int tok_base = (tile0 + it) * kST;
+      // ---- phase 1
+      {
+        uint64_t dot2[HS];
+#pragma unroll
+        for (int i = 0; i < HS; ++i) dot2[i] = 0ull;
+        const float x0 = lds32(tile_chunk(tile, tok_l, 0));
+        const uint64_t nx0 = f2_pack(-x0, -x0);
+        uint64_t s1 = 0ull, s2 = 0ull;
+#pragma unroll 4
+        for (int c = 0; c < 24; ++c) {
+          const int c4 = c_base + 2 * c;
+          const float4 t = lds128(tile_chunk(tile, tok_l, c4));
+          const uint64_t t01 = f2_pack(t.x, t.y), t23 = f2_pack(t.z, t.w);
+          const uint64_t a01 = f2_add(t01, nx0), a23 = f2_add(t23, nx0);
+          s1 = f2_add(s1, f2_add(a01, a23));
+          s2 = f2_fma(a01, a01, f2_fma(a23, a23, s2));
+#pragma unroll
+          for (int i = 0; i < HS; ++i) {
+            const float4 gv = lds128(g_u + (i * kSD + c4 * 4) * 4);
+            dot2[i] = f2_fma(t01, f2_pack(gv.x, gv.y), f2_fma(t23, f2_pack(gv.z, gv.w), dot2[i]));
+          }
+        }
+        float dot[HS];
+#pragma unroll
+        for (int i = 0; i < HS; ++i) {
+          dot[i] = f2_lo(dot2[i]) + f2_hi(dot2[i]);
+          dot[i] += __shfl_xor_sync(0xffffffffu, dot[i], 16);
+        }
+        float s1f = f2_lo(s1) + f2_hi(s1), s2f = f2_lo(s2) + f2_hi(s2);
+        s1f += __shfl_xor_sync(0xffffffffu, s1f, 16);
+        s2f += __shfl_xor_sync(0xffffffffu, s2f, 16);
+        if (half == 0) {
+          const uint32_t pp = part_u + ((warp * kST + tok_l) * Cfg::PART_STRIDE) * 4;
+#pragma unroll
+          for (int i = 0; i < HS; ++i) sts32(pp + 4 * i, dot[i]);
+          sts32(pp + 4 * HS, s1f);
+          sts32(pp + 4 * HS + 4, s2f);
+          sts32(pp + 4 * HS + 8, x0);
+        }
+      }
+      // this warp is done with the token tile
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tile_empty[st]);
+      named_bar_sync(1, 128);                                   // partials of all four group-A warps are visible
+      // ---- phase 1b: thread <-> (token, slot) of one head
+      const int buf = it & 1;
+      mbar_wait(&w_empty[buf], ((it >> 1) & 1) ^ 1);
+#pragma unroll
+      for (int k = 0; k < UPW; ++k) {
+        const int unit = warp + 4 * k;
+        const int h = unit % 4, tg = unit / 4;
+        const int s_l = lane / TPW, tk = tg * TPW + (lane % TPW);
+        const int sh = h * S + s_l;
+        float dot = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          const uint32_t pp = part_u + ((w * kST + tk) * Cfg::PART_STRIDE) * 4;
+          dot += lds32(pp + 4 * sh);
+          s1 += lds32(pp + 4 * HS);
+          s2 += lds32(pp + 4 * HS + 4);
+        }
+        const float x0 = lds32(part_u + (tk * Cfg::PART_STRIDE) * 4 + 4 * HS + 8);
+        const float d1 = s1 * (1.0f / kSD);
+        const float mu = x0 + d1;
+        const float r = rsqrtf(fmaxf(s2 * (1.0f / kSD) - d1 * d1, 0.f) + p.eps);
+        const int tok = tok_base + tk;
+        const bool valid = tok < p.N;
+        const float logit = fmaf(r, dot - mu * __ldg(p.G + b * HS + sh), __ldg(p.c0 + b * HS + sh));
+        float mx = logit;
+#pragma unroll
+        for (int o = TPW; o < 32; o <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        const float e = expf(logit - mx);
+        float sum = e;
+#pragma unroll
+        for (int o = TPW; o < 32; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float a = valid ? e / sum : 0.f;
+        const float w = a * r;
+        const uint32_t wp = w_u + ((buf * kST + tk) * HS + sh) * 8;
+        sts32(wp, w);
+        sts32(wp + 4, w);
+        accA[k] += a;
+        accM[k] = fmaf(w, mu, accM[k]);
+        if (valid) {
+          if (p.attn != nullptr) p.attn[((long long)b * HS + sh) * p.N + tok] = a;
+          if (p.mu != nullptr && s_l == 0 && h == 0) { p.mu[(long long)b * p.N + tok] = mu; p.rstd[(long long)b * p.N + tok] = r; }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&w_full[buf]);
+      named_bar_sync(1, 128);                                   // partial[] may be overwritten by the next tile
+    }
+#pragma unroll
+    for (int k = 0; k < UPW; ++k) {
+      float a = accA[k], mm = accM[k];
+#pragma unroll
+      for (int o = 1; o < TPW; o <<= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        mm += __shfl_xor_sync(0xffffffffu, mm, o);
+      }
+      if (lane % TPW == 0) {
+        const int unit = warp + 4 * k;
+        const int sh = (unit % 4) * S + lane / TPW;
+        atomicAdd(p.A + b * HS + sh, a);
+        atomicAdd(p.m + b * HS + sh, mm);
+      }
+    }
+  } else {
+    // =============================================================== group B
+    const int u = tid - 128;                                    // owns channel pairs 2u, 256 + 2u, 512 + 2u
+    uint64_t acc[HS][3];
+#pragma unroll
+    for (int i = 0; i < HS; ++i) acc[i][0] = acc[i][1] = acc[i][2] = 0ull;
+    const int cchunk = u >> 1;                                  // 16-byte chunk index of the first pair (0..63)
+    const int cin = (u & 1) * 8;                                // byte offset inside the chunk
+    for (int it = 0; it < ntiles; ++it) {
+      const int st = it % Cfg::STAGES, buf = it & 1;
+      mbar_wait(&full[st], (it / Cfg::STAGES) & 1);
+      mbar_wait(&w_full[buf], (it >> 1) & 1);
+      const uint32_t tile = smem_u32(smem + Cfg::OFF_TILE + st * kSTileBytes);
+#pragma unroll 4
+      for (int j = 0; j < kST; ++j) {
+        uint64_t t[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const float2 v = lds64(tile_chunk(tile, j, cchunk + 64 * k) + cin);
+          t[k] = f2_pack(v.x, v.y);
+        }
+        const uint32_t wj = w_u + ((buf * kST + j) * HS) * 8;
+#pragma unroll
+        for (int i2 = 0; i2 < HS / 2; ++i2) {
+          const float4 wv = lds128(wj + 16 * i2);               // (w[2 i2], w[2 i2]), (w[2 i2 + 1], w[2 i2 + 1])
+          const uint64_t w0 = f2_pack(wv.x, wv.y), w1 = f2_pack(wv.z, wv.w);
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            acc[2 * i2][k] = f2_fma(w0, t[k], acc[2 * i2][k]);
+            acc[2 * i2 + 1][k] = f2_fma(w1, t[k], acc[2 * i2 + 1][k]);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&tile_empty[st]);
+        mbar_arrive(&w_empty[buf]);
+      }
+    }
+    float* dst = p.U + (long long)b * HS * kSD + 2 * u;
+#pragma unroll
+    for (int i = 0; i < HS; ++i) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        atomicAdd(dst + i * kSD + 256 * k, f2_lo(acc[i][k]));
+        atomicAdd(dst + i * kSD + 256 * k + 1, f2_hi(acc[i][k]));
+      }
+    }
+  }
+}
+
+// =====================================================================================================================
 // Backward of the streaming step.  Saved from the forward: the slot-softmax a[sh, j] and the token statistics (mu, r).
 //   f[sh]    = dU[sh] . t_j + dm[sh] mu_j                      e[sh] = g[sh] . t_j - mu_j G[sh]
 //   da[sh]   = r_j f[sh] + dA[sh] + dattn[sh, j]
@@ -499,18 +741,19 @@ static int make_token_tmap(CUtensorMap* tm, const float* tokens, int B, int N) {
   return make_tmap_nd(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, tokens, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-template <int HS>
+template <int HS, bool V2>
 static int launch_slot_fwd(const CUtensorMap& tm, const SlotParams& p, int splits, cudaStream_t s) {
-  using Cfg = SlotCfg<HS>;
-  auto kern = slot_stream_fwd_kernel<HS>;
+  constexpr int kBytes = V2 ? SlotCfg2<HS>::BYTES : SlotCfg<HS>::BYTES;
+  static_assert(kBytes <= 227 * 1024, "slot forward does not fit in shared memory");
+  auto kern = V2 ? slot_stream_fwd2_kernel<HS> : slot_stream_fwd_kernel<HS>;
   static bool attr_done = false;
   if (!attr_done) {
-    DV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::BYTES));
+    DV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kBytes));
     attr_done = true;
   }
   const double bytes = (double)p.B * p.N * kSD * 4 + (p.attn ? (double)p.B * HS * p.N * 4 : 0.0);
   const int prof = prof_begin(DEVIAS_PROF_SLOT, bytes, s);
-  kern<<<dim3(splits, p.B), kSlotThreads, Cfg::BYTES, s>>>(tm, p);
+  kern<<<dim3(splits, p.B), kSlotThreads, kBytes, s>>>(tm, p);
   prof_end(prof, s);
   DV_CHECK_CUDA(cudaGetLastError());
   count_launch();
@@ -541,9 +784,9 @@ extern "C" int devias_slot_stream_fwd(const float* tokens, const float* g, const
   splits = (tiles + per - 1) / per;
   SlotParams p{batch, n_tokens, num_slots, per, tiles, g, G, c0, U, m, A, attn, mu, rstd, eps};
   switch (num_slots) {
-    case 2: return launch_slot_fwd<8>(tm, p, splits, s);
-    case 4: return launch_slot_fwd<16>(tm, p, splits, s);
-    default: return launch_slot_fwd<32>(tm, p, splits, s);
+    case 2: return launch_slot_fwd<8, true>(tm, p, splits, s);
+    case 4: return launch_slot_fwd<16, true>(tm, p, splits, s);
+    default: return launch_slot_fwd<32, false>(tm, p, splits, s);
   }
 }
 

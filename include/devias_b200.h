@@ -2,7 +2,7 @@
  * devias_b200 -- C-ABI of the B200-native DEVIAS hot path (sm_100a).
  *
  * The reference (KHU-VLL/DEVIAS) is pure PyTorch and has no FFI of its own; its "operator interface"
- * for this path is the set of torch library calls made by model/modeling_slot.py and agg_block/*.py
+ * for this path is the set of torch library calls made by model/modeling_slot.py and the agg_block modules
  * (SURVEY.md section 2.2).  Each entry point below replaces one of those call sites and cites it.
  * All pointers are DEVICE pointers owned by the caller (PyTorch); no entry point allocates, synchronises
  * or touches the host copy of the data.  `stream` is a cudaStream_t passed as void*.
