@@ -300,6 +300,29 @@ def main():
         barrier()
         e2e_ms = e0.elapsed_time(e1)
 
+    # ---------------------------------------------------------------- slot-attention micro-measure (BASELINE config 5)
+    slot_micro = None
+    if rank == 0:
+        try:
+            from devias_b200 import ops as _ops
+            Bm, Sm = 128, cfg['num_latents']
+            tok = torch.randn(Bm, 1568, 768, device=dev) * 1.5
+            g_ = torch.randn(Bm, 4 * Sm, 768, device=dev) * 0.05
+            G_ = g_.sum(-1).contiguous(); c0_ = torch.randn(Bm, 4 * Sm, device=dev)
+            for _ in range(3):
+                _ops.slot_stream_fwd(tok, g_, G_, c0_)
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(); s0.record()
+            for _ in range(10):
+                _ops.slot_stream_fwd(tok, g_, G_, c0_)
+            s1.record(); torch.cuda.synchronize()
+            t_ms = s0.elapsed_time(s1) / 10
+            slot_micro = {'batch': Bm, 'slots': Sm, 'tokens_dtype': 'f32', 'us_per_pass': t_ms * 1e3,
+                          'gbs': Bm * 1568 * 768 * 4 / (t_ms * 1e-3) / 1e9}
+            del tok, g_, G_, c0_
+        except Exception as e:  # the micro-measure must never take the headline down
+            slot_micro = {'error': repr(e)}
+
     # ---------------------------------------------------------------- max over ranks
     t = torch.tensor([ms, e2e_ms or 0.0], device=dev, dtype=torch.float64)
     if world > 1:
@@ -335,7 +358,9 @@ def main():
                          'launches': int(gemm_n), 'share_of_step': gemm_ms / eager_ms, 'timed_over': 'eager re-run of the timed steps',
                          'eager_ms_per_step': eager_ms / args.steps,
                          'attention': {'tflops': attn_flops / (attn_ms * 1e-3) / 1e12 if attn_ms > 0 else None, 'share_of_step': attn_ms / eager_ms, 'launches': int(attn_n)},
-                         'slot_attention': {'gbs': slot_bytes / (slot_ms * 1e-3) / 1e9 if slot_ms > 0 else None, 'peak_gbs': peak_gbs, 'share_of_step': slot_ms / eager_ms, 'launches': int(slot_n)},
+                         'slot_attention': {'in_step_gbs': slot_bytes / (slot_ms * 1e-3) / 1e9 if slot_ms > 0 else None, 'peak_gbs': peak_gbs,
+                                            'share_of_step': slot_ms / eager_ms, 'launches': int(slot_n), 'microbench': slot_micro,
+                                            'microbench_frac_of_hbm': (slot_micro['gbs'] / peak_gbs) if slot_micro and 'gbs' in slot_micro else None},
                          'step_tensor_frac': value / world * TRAIN_GFLOP_PER_CLIP / 1e3 / peak_tf},
         }
         if e2e_ms:
