@@ -115,6 +115,16 @@ def synth_state_dict(num_classes=101, num_scene_classes=365, num_latents=2, agg_
     return sd
 
 
+def synth_teacher_state_dict(num_classes=365, depth=12, seed=0) -> State:
+    """state_dict of the frozen scene teacher `vit_base_patch16_224(num_classes=365, use_mean_pooling=False)`
+    (model/modeling_finetune.py:178-334): the student's encoder keys plus cls_token and a 365-way head."""
+    full = synth_state_dict(num_classes=1, num_scene_classes=num_classes - 1, depth=depth, seed=seed + 500)
+    sd = {k: v for k, v in full.items() if k.startswith(('patch_embed.', 'blocks.', 'norm.', 'head.'))}
+    rs = np.random.RandomState(seed + 501)
+    sd['cls_token'] = _trunc_normal(rs, (1, 1, 768), 0.02)
+    return sd
+
+
 def synth_clips(batch: int, seed=0, frames=16, size=224) -> Tensor:
     """N(0,1) clips [B,3,T,H,W] fp32 (ImageNet-normalised video is ~zero-mean/unit-var;
     dataset/kinetics.py:80-86).  numpy RandomState => identical on every machine."""
@@ -195,6 +205,21 @@ def forward_features(sd: State, clips: Tensor, depth: Optional[int] = None, num_
         x = encoder_block(sd, i, x, num_heads, eps)
     D = x.shape[-1]
     return F.layer_norm(x, (D,), sd['norm.weight'], sd['norm.bias'], eps)
+
+
+def teacher_forward(sd: State, clips: Tensor, depth: Optional[int] = None, num_heads=12, eps=1e-6):
+    """model/modeling_finetune.py:270-325 with use_mean_pooling=False: CLS token prepended, 1569-row sinusoid table,
+    blocks, LayerNorm, x[:, 0] -> head.  Returns (token [B,768], logits [B,365])."""
+    x = patch_embed(sd, clips)
+    x = torch.cat((sd['cls_token'].expand(x.shape[0], -1, -1), x), dim=1)
+    x = x + sinusoid_table(x.shape[1], x.shape[2]).type_as(x)
+    if depth is None:
+        depth = 1 + max(int(k.split('.')[1]) for k in sd if k.startswith('blocks.'))
+    for i in range(depth):
+        x = encoder_block(sd, i, x, num_heads, eps)
+    x = F.layer_norm(x, (x.shape[-1],), sd['norm.weight'], sd['norm.bias'], eps)
+    token = x[:, 0]
+    return token, F.linear(token, sd['head.weight'], sd['head.bias'])
 
 
 # ----------------------------------------------------------------------------------------------

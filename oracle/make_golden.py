@@ -128,6 +128,19 @@ def main():
     np.savez_compressed(os.path.join(OUT, name + '.npz'), depth=depth, S=S, agg_depth=d, tied=tied, C=C, batch=B, **rec)
     print(name, loss.item(), total.item(), parts)
 
+    # frozen scene teacher (model/modeling_finetune.py), CLS token, 365 classes
+    import importlib
+    mf = importlib.import_module('model.modeling_finetune')
+    tsd = O.synth_teacher_state_dict(seed=6)
+    with contextlib.redirect_stdout(io.StringIO()):
+        tm = mf.vit_base_patch16_224(num_classes=365, use_mean_pooling=False, init_scale=1.0)
+    assert set(tm.state_dict().keys()) == set(tsd.keys())
+    tm.load_state_dict(tsd); tm.eval()
+    with torch.no_grad():
+        tok, logit = tm(O.synth_clips(1, seed=3))
+    np.savez_compressed(os.path.join(OUT, 'teacher_d12.npz'), token=_np(tok), logits=_np(logit))
+    print('teacher', float(logit.abs().max()))
+
     # sinusoid table known answers
     tab = ns.modeling_slot.get_sinusoid_encoding_table(1568, 768)
     np.savez_compressed(os.path.join(OUT, 'sinusoid.npz'), rows=_np(tab[0, [0, 1, 2, 777, 1567]]), sum=np.float64(tab.double().sum().item()))

@@ -147,3 +147,18 @@ def test_state_dict_roundtrip_and_weight_refresh():
     assert torch.allclose(b, c, rtol=1e-4, atol=1e-5)   # identical weights -> identical logits (up to atomic summation order)
     with pytest.raises(RuntimeError):
         mk()(x.cpu())   # no CPU fallback
+
+
+def test_teacher_bf16_vs_golden():
+    """frozen scene teacher: CLS token, 1569 tokens, same kernels"""
+    from devias_b200.modeling_finetune import vit_base_patch16_224
+    g = golden('teacher_d12')
+    sd = O.synth_teacher_state_dict(seed=6)
+    m = _quiet(vit_base_patch16_224, num_classes=365, use_mean_pooling=False, init_scale=1.0)
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    with torch.no_grad():
+        tok, logit = m(O.synth_clips(1, seed=3).cuda(), return_attn=False)
+    assert_close(tok, g['token'], E2E_TOL, 'teacher token')
+    assert_close(logit, g['logits'], E2E_TOL, 'teacher logits')
+    assert int(logit.argmax()) == int(g['logits'].argmax())

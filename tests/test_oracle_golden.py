@@ -109,3 +109,13 @@ def test_oracle_vs_live_reference():
     assert_close(o[1][2], r[1][2], TOL, 'attn')
     assert_close(o[2][1], r[2][1], TOL, 'slots')
     assert_close(o[2][2], r[2][2], TOL, 'mask')
+
+
+def test_teacher_forward_golden():
+    g = golden('teacher_d12')
+    sd = O.synth_teacher_state_dict(seed=6)
+    with torch.no_grad():
+        tok, logit = O.teacher_forward(sd, O.synth_clips(1, seed=3))
+    assert_close(tok, g['token'], TOL, 'teacher token')
+    assert_close(logit, g['logits'], TOL, 'teacher logits')
+    assert int(logit.argmax()) == int(g['logits'].argmax())
