@@ -261,8 +261,9 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 //   dV += P^T dO_i,  dK += dS^T Q_i   (the P / dS tiles are read as MN-major A operands),   dQ_i = dS K
 // The softmax scale is applied to dK in the epilogue and to dQ in the fp32 -> bf16 conversion kernel.
 //   warp 0 : TMA (K,V once; Q_i, dO_i through a 2-stage ring)   warp 1 : tcgen05 issuer
-//   warps 2..9 : compute (query-row quarter = warp % 4, key-column half = (warp - 2) / 4)
-constexpr int kBwdThreads = 320;
+//   warps 2..17 : compute (query-row quarter = warp % 4, 32-key column group = (warp - 2) / 4): four warps per scheduler
+//                 hide the TMEM / MUFU / shared-memory latencies of the recompute chain (8 warps left it latency-bound)
+constexpr int kBwdThreads = 576;   // TMA warp + MMA warp + 16 compute warps (4 per TMEM lane quarter)
 struct FbSmem {
   static constexpr int TILE = 128 * kHD * 2;            // 16 KiB: a [128 x 64] bf16 operand tile
   static constexpr int OFF_K = 0;
@@ -281,7 +282,9 @@ struct FbParams {
   float scale, scale_log2;
   const float* lse2; const float* delta;   // [B, H, Npad]
   __nv_bfloat16* dqkv; long long ld;        // [B*N, 3*H*64]
+  long long* dbg;                           // DEVIAS_FLASH_DEBUG=1: per-phase SM clock stamps of CTA 0 (timeline debugging)
 };
+#define FB_STAMP(slot) do { if (p.dbg != nullptr && blockIdx.x == 0 && i < 8) p.dbg[(slot) * 8 + i] = clock64(); } while (0)
 
 __global__ void __launch_bounds__(kBwdThreads, 1)
 flash_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
@@ -322,8 +325,8 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1);
         mbar_init(&dq_full[i], 1); mbar_init(&dq_empty[i], 8);
       }
-      mbar_init(sdp_full, 1); mbar_init(sdp_empty, 8);
-      mbar_init(pds_full, 8); mbar_init(pds_empty, 1);
+      mbar_init(sdp_full, 1); mbar_init(sdp_empty, 16);
+      mbar_init(pds_full, 16); mbar_init(pds_empty, 1);
       mbar_init(acc_full, 1);
       fence_barrier_init();
     }
@@ -375,9 +378,12 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
       mbar_wait(kv_full, 0);
       issue_sdp(0);
       for (int i = 0; i < T; ++i) {
+        FB_STAMP(0);
         if (i + 1 < T) issue_sdp(i + 1);
+        FB_STAMP(1);
         const int st = i & 1;
         mbar_wait(pds_full, i & 1);
+        FB_STAMP(2);
         tc_fence_after();
         // P / dS tiles: [128 query rows][2 key atoms of 64]; read MN-major: M = keys (atoms 16 KiB apart), K = query rows
         const uint64_t ap_mn = umma_desc_sw128(sp, FbSmem::TILE, 1024), ads_mn = umma_desc_sw128(sds, FbSmem::TILE, 1024);
@@ -401,25 +407,28 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         umma_commit(&dq_full[i & 1]);
         umma_commit(pds_empty);
         umma_commit(&qdo_empty[st]);
+        FB_STAMP(3);
       }
       umma_commit(acc_full);
     }
     __syncwarp();
   } else {
-    const int cw = warp - 2;                 // 0..7
+    const int cw = warp - 2;                 // 0..15
     const int q4 = warp & 3;                 // TMEM lane quarter = query-row quarter
-    const int g = cw >> 2;                   // key-column half
+    const int cg = cw >> 2;                  // 32-key column group
     const int lane = (int)lane_id();
     const int r = q4 * 32 + lane;            // query row inside the tile (S/dP/dQ) or key row (epilogue)
     const uint32_t lane_sel = (uint32_t)(q4 * 32) << 16;
-    const uint32_t prow = smem_u32(smem + FbSmem::OFF_P + g * FbSmem::TILE + r * 128);
-    const uint32_t dsrow = smem_u32(smem + FbSmem::OFF_DS + g * FbSmem::TILE + r * 128);
-    uint8_t* dq_box_p = smem + FbSmem::OFF_DQ + cw * 4096;
+    const uint32_t prow = smem_u32(smem + FbSmem::OFF_P + (cg >> 1) * FbSmem::TILE + r * 128);
+    const uint32_t dsrow = smem_u32(smem + FbSmem::OFF_DS + (cg >> 1) * FbSmem::TILE + r * 128);
+    const int g = cg;                        // dQ column half handled by the warps with cg < 2
+    uint8_t* dq_box_p = smem + FbSmem::OFF_DQ + (cw & 7) * 4096;
     const uint32_t dq_box = smem_u32(dq_box_p);
     const long long stat_row = ((long long)b * p.H + h) * p.Npad;
     const uint64_t cc = f2_pack(p.scale_log2, p.scale_log2);
     auto reduce_dq = [&](int i) {
       // dQ_i rows of this warp, columns [32 g, 32 g + 32): TMEM -> swizzled smem box -> TMA reduce-add (fp32, at L2)
+      if (cg >= 2) return;
       tc_fence_after();
       uint32_t t[32];
       tmem_ld_32x32b_x32(tm_dq[i & 1] + lane_sel + 32 * g, t);
@@ -445,68 +454,67 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
       const float lse = __ldg(p.lse2 + stat_row + qi);        // padded rows: +inf -> P = 0
       const float del = __ldg(p.delta + stat_row + qi);       // padded rows: 0
       const uint64_t nl = f2_pack(-lse, -lse), nd = f2_pack(-del, -del);
+      if (warp == 2 && lane == 0) FB_STAMP(4);
       mbar_wait(sdp_full, i & 1);
+      if (warp == 2 && lane == 0) FB_STAMP(5);
       tc_fence_after();
-      uint32_t pp[32], dd[32];                     // packed bf16x2: P and dS for this thread's 64 keys
+      uint32_t pp[16], dd[16];                     // packed bf16x2: P and dS for this thread's 32 keys
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
-        uint32_t sv_[32], dp_[32];
-        tmem_ld_32x32b_x32(tm_s + lane_sel + 64 * g + 32 * c, sv_);
-        tmem_ld_32x32b_x32(tm_dp + lane_sel + 64 * g + 32 * c, dp_);
+        uint32_t sv_[16], dp_[16];
+        tmem_ld_32x32b_x16(tm_s + lane_sel + 32 * cg + 16 * c, sv_);
+        tmem_ld_32x32b_x16(tm_dp + lane_sel + 32 * cg + 16 * c, dp_);
         tmem_ld_wait();
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
+        for (int k = 0; k < 8; ++k) {
           const uint64_t x = f2_fma(f2_pack(__uint_as_float(sv_[2 * k]), __uint_as_float(sv_[2 * k + 1])), cc, nl);
           const float p0 = fast_exp2(f2_lo(x)), p1 = fast_exp2(f2_hi(x));
           const uint64_t pv = f2_pack(p0, p1);
           const uint64_t ds = f2_mul(pv, f2_add(f2_pack(__uint_as_float(dp_[2 * k]), __uint_as_float(dp_[2 * k + 1])), nd));
-          pp[16 * c + k] = pack_bf16(p0, p1);
-          dd[16 * c + k] = pack_bf16(f2_lo(ds), f2_hi(ds));
+          pp[8 * c + k] = pack_bf16(p0, p1);
+          dd[8 * c + k] = pack_bf16(f2_lo(ds), f2_hi(ds));
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(sdp_empty);
+      if (warp == 2 && lane == 0) FB_STAMP(6);
       // dQ_{i-1} is the last MMA of tile i-1: once it has retired, P / dS of tile i-1 have been consumed as well
       if (i > 0) mbar_wait(&dq_full[(i - 1) & 1], ((i - 1) >> 1) & 1);
+      if (warp == 2 && lane == 0) FB_STAMP(7);
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const int off = (c ^ (r & 7)) << 4;
+      for (int c = 0; c < 4; ++c) {
+        const int off = (((cg & 1) * 4 + c) ^ (r & 7)) << 4;
         sts128(prow + off, pp[4 * c], pp[4 * c + 1], pp[4 * c + 2], pp[4 * c + 3]);
         sts128(dsrow + off, dd[4 * c], dd[4 * c + 1], dd[4 * c + 2], dd[4 * c + 3]);
       }
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(pds_full);
+      if (warp == 2 && lane == 0) FB_STAMP(8);
       if (i > 0) reduce_dq(i - 1);
+      if (warp == 2 && lane == 0) FB_STAMP(9);
     }
     mbar_wait(&dq_full[(T - 1) & 1], ((T - 1) >> 1) & 1);
     reduce_dq(T - 1);
-    // epilogue: dK (scaled) and dV rows of this key tile (thread = key row)
+    // epilogue: dK (scaled) and dV rows of this key tile (thread = key row; 32 of the 64 columns per warp)
     mbar_wait(acc_full, 0);
     tc_fence_after();
     const int ki = k0 + r;
     {
-      uint32_t t0[32], t1[32];
-      const uint32_t src = (g == 0 ? tm_dk : tm_dv) + lane_sel;
-      tmem_ld_32x32b_x32(src, t0);
-      tmem_ld_32x32b_x32(src + 32, t1);
+      const bool is_dk = cg < 2;
+      uint32_t t0[32];
+      tmem_ld_32x32b_x32((is_dk ? tm_dk : tm_dv) + lane_sel + 32 * (cg & 1), t0);
       tmem_ld_wait();
       if (ki < p.N) {
-        const float sc = g == 0 ? p.scale : 1.0f;
-        uint4* dst = reinterpret_cast<uint4*>(p.dqkv + ((long long)b * p.N + ki) * p.ld + (g == 0 ? D : 2 * D) + h * kHD);
+        const float sc = is_dk ? p.scale : 1.0f;
+        uint4* dst = reinterpret_cast<uint4*>(p.dqkv + ((long long)b * p.N + ki) * p.ld + (is_dk ? D : 2 * D) + h * kHD + 32 * (cg & 1));
 #pragma unroll
         for (int c = 0; c < 4; ++c)
           dst[c] = make_uint4(pack_bf16(sc * __uint_as_float(t0[8 * c]), sc * __uint_as_float(t0[8 * c + 1])),
                               pack_bf16(sc * __uint_as_float(t0[8 * c + 2]), sc * __uint_as_float(t0[8 * c + 3])),
                               pack_bf16(sc * __uint_as_float(t0[8 * c + 4]), sc * __uint_as_float(t0[8 * c + 5])),
                               pack_bf16(sc * __uint_as_float(t0[8 * c + 6]), sc * __uint_as_float(t0[8 * c + 7])));
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          dst[4 + c] = make_uint4(pack_bf16(sc * __uint_as_float(t1[8 * c]), sc * __uint_as_float(t1[8 * c + 1])),
-                                  pack_bf16(sc * __uint_as_float(t1[8 * c + 2]), sc * __uint_as_float(t1[8 * c + 3])),
-                                  pack_bf16(sc * __uint_as_float(t1[8 * c + 4]), sc * __uint_as_float(t1[8 * c + 5])),
-                                  pack_bf16(sc * __uint_as_float(t1[8 * c + 6]), sc * __uint_as_float(t1[8 * c + 7])));
       }
     }
     if (lane == 0) bulk_wait0();
@@ -632,8 +640,14 @@ extern "C" int devias_flash_attn_bwd(const void* qkv, const void* out, const voi
                                                                   static_cast<const __nv_bfloat16*>(dout), delta_ws, batch, seq,
                                                                   heads, Npad);
   }
+  static long long* dbg_dev = nullptr;
+  const bool dbg_on = getenv("DEVIAS_FLASH_DEBUG") != nullptr;
+  if (dbg_on && dbg_dev == nullptr) {
+    DV_CHECK_CUDA(cudaMalloc(&dbg_dev, 10 * 8 * sizeof(long long)));
+    DV_CHECK_CUDA(cudaMemset(dbg_dev, 0, 10 * 8 * sizeof(long long)));
+  }
   FbParams p{batch, seq, heads, Npad, scale, scale * 1.4426950408889634f, lse2, delta_ws,
-             static_cast<__nv_bfloat16*>(dqkv), (long long)3 * D};
+             static_cast<__nv_bfloat16*>(dqkv), (long long)3 * D, dbg_on ? dbg_dev : nullptr};
   const int k_tiles = (seq + 127) / 128;
   const int prof = prof_begin(DEVIAS_PROF_ATTN, 10.0 * batch * heads * (double)seq * seq * kHD, s);
   flash_bwd_kernel<<<batch * heads * k_tiles, kBwdThreads, FbSmem::BYTES, s>>>(tmQKV, tmDO, tmDQ, p);
@@ -646,6 +660,22 @@ extern "C" int devias_flash_attn_bwd(const void* qkv, const void* out, const voi
                                                         (long long)3 * D, scale);
   }
   DV_CHECK_CUDA(cudaGetLastError());
+  if (dbg_on) {
+    long long hst[80];
+    DV_CHECK_CUDA(cudaDeviceSynchronize());
+    DV_CHECK_CUDA(cudaMemcpy(hst, dbg_dev, sizeof(hst), cudaMemcpyDeviceToHost));
+    static int printed = 0;
+    if (printed++ < 2) {
+      const char* names[10] = {"mma: loop top", "mma: S/dP(i+1) issued", "mma: pds_full seen", "mma: dV dK dQ issued", "cmp: wait sdp_full",
+                               "cmp: sdp_full seen", "cmp: reads+math done", "cmp: dq_full(i-1) seen", "cmp: P/dS written", "cmp: dQ reduced"};
+      const long long t0 = hst[4 * 8 + 0];
+      for (int sl = 0; sl < 10; ++sl) {
+        printf("%-24s", names[sl]);
+        for (int i = 0; i < 8; ++i) printf(" %7lld", hst[sl * 8 + i] - t0);
+        printf("\n");
+      }
+    }
+  }
   count_launch(3);
   return DEVIAS_OK;
 }
