@@ -125,12 +125,13 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       for (int j = 0; j < T; ++j) {
         if (j + 1 < T) issue_s(j + 1);
         const int st = j % kKVStages;
-        mbar_wait(&p_full[j & 1], (j >> 1) & 1);   // P_j is in smem and any rescaling of O (tcgen05.st) has been fenced
+        mbar_wait(&p_full[j & 1], (j >> 1) & 1);   // P_j is in TMEM and any rescaling of O (tcgen05.st) has been fenced
         tc_fence_after();
-        const uint64_t da = umma_desc_sw128(smem_u32(smem + FaSmem::OFF_P + (j & 1) * FaSmem::P_BYTES), 0, 1024);
+        // A = P_j straight from tensor memory (bf16 pairs packed over the first 32 columns of the S_j buffer): the
+        // shared-memory port, which bounds this head_dim-64 kernel, only carries the V operand
         const uint64_t db = umma_desc_sw128(smem_u32(smem + FaSmem::OFF_V + st * FaSmem::V_BYTES), kKT * 128, 1024);
 #pragma unroll
-        for (int k = 0; k < kKT / 16; ++k) umma_ss(tm_o, da + 2 * k, db + 128 * k, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+        for (int k = 0; k < kKT / 16; ++k) umma_ts(tm_o, tm_s[j & 1] + 8 * k, db + 128 * k, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
         umma_commit(&pv_done[j & 3]);
         umma_commit(&kv_empty[st]);
       }
@@ -191,14 +192,11 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         m = m_run;
       }
       const uint64_t negm = f2_pack(-m, -m);
-      // P_j -> smem (K-major, 128B swizzle: 16-byte chunk c of row r lands at chunk c ^ (r & 7))
-      // P buffer (j & 1) is free: S_j was issued after P_{j-2} V_{j-2} and the tensor pipe retires in order, so the
-      // s_full wait above already implies it.
-      const uint32_t prow = p_row_base + (j & 1) * FaSmem::P_BYTES;
+      // P_j (bf16 pairs) -> tensor memory, over the S_j columns this thread has already consumed (lane = query row)
       uint64_t sum2[4] = {0ull, 0ull, 0ull, 0ull};
+      uint32_t pk[32];
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
-        uint32_t pk[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int e = 8 * (c & 3) + 2 * i;
@@ -207,13 +205,13 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           const uint64_t y = f2_fma(x, cc, negm);
           const float e0 = fast_exp2(f2_lo(y)), e1 = fast_exp2(f2_hi(y));
           sum2[i] = f2_add(sum2[i], f2_pack(e0, e1));
-          pk[i] = pack_bf16(e0, e1);
+          pk[4 * c + i] = pack_bf16(e0, e1);
         }
-        sts128(prow + ((c ^ (r & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
       }
+      tmem_st_32x32b_x32(tm_s[j & 1] + lane_sel, pk);
       const uint64_t st = f2_add(f2_add(sum2[0], sum2[1]), f2_add(sum2[2], sum2[3]));
       l += f2_lo(st) + f2_hi(st);
-      fence_proxy_async();
+      tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[j & 1]);
