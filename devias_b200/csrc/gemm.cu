@@ -295,13 +295,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 }
                 if constexpr (EPI == DEVIAS_EPI_DGELU_BF16) {
                   const float2 h0 = unpack_bf16(aux[hlf * 16 + 2 * i]), h1 = unpack_bf16(aux[hlf * 16 + 2 * i + 1]);
-                  v.x *= gelu_fast_grad(h0.x); v.y *= gelu_fast_grad(h0.y); v.z *= gelu_fast_grad(h1.x); v.w *= gelu_fast_grad(h1.y);
+                  const uint64_t g0 = f2_mul(f2_pack(v.x, v.y), gelu_grad_pair(f2_pack(h0.x, h0.y)));
+                  const uint64_t g1 = f2_mul(f2_pack(v.z, v.w), gelu_grad_pair(f2_pack(h1.x, h1.y)));
+                  v.x = f2_lo(g0); v.y = f2_hi(g0); v.z = f2_lo(g1); v.w = f2_hi(g1);
                 }
                 outv[hlf * 16 + 2 * i] = pack_bf16(v.x, v.y);
                 outv[hlf * 16 + 2 * i + 1] = pack_bf16(v.z, v.w);
                 if constexpr (ET::TWO_OUT) {
-                  outv2[hlf * 16 + 2 * i] = pack_bf16(gelu_fast(v.x), gelu_fast(v.y));
-                  outv2[hlf * 16 + 2 * i + 1] = pack_bf16(gelu_fast(v.z), gelu_fast(v.w));
+                  const uint64_t a0 = gelu_pair(f2_pack(v.x, v.y)), a1 = gelu_pair(f2_pack(v.z, v.w));
+                  outv2[hlf * 16 + 2 * i] = pack_bf16(f2_lo(a0), f2_hi(a0));
+                  outv2[hlf * 16 + 2 * i + 1] = pack_bf16(f2_lo(a1), f2_hi(a1));
                 }
               }
             }
