@@ -37,9 +37,15 @@ class GradReducer:
             cur_n += n
         if cur:
             groups.append(cur)
+        sizes = [sum((p.numel() + 7) // 8 * 8 for p in g) for g in groups]
+        # all buckets are slices of ONE arena, so the un-overlapped path can exchange everything with a single collective
+        self.arena = torch.zeros(sum(sizes), device=params[0].device, dtype=torch.float32)
+        self._avg = dist.is_initialized() and dist.get_backend(process_group) == 'nccl'   # NCCL averages natively
+        start = 0
         for bi, g in enumerate(groups):
-            total = sum((p.numel() + 7) // 8 * 8 for p in g)
-            flat = torch.zeros(total, device=g[0].device, dtype=torch.float32)
+            total = sizes[bi]
+            flat = self.arena[start:start + total]
+            start += total
             off = 0
             for p in g:
                 self._views[p] = flat[off:off + p.numel()].view(p.shape)
@@ -57,8 +63,7 @@ class GradReducer:
     # ------------------------------------------------------------------------------------------
     def zero_grad(self):
         """replaces optimizer.zero_grad(): one memset per bucket, .grad views stay attached"""
-        for flat in self.buckets:
-            flat.zero_()
+        self.arena.zero_()
         for p in self.params:
             if p.grad is None or p.grad.data_ptr() != self._views[p].data_ptr():
                 p.grad = self._views[p]
@@ -80,7 +85,8 @@ class GradReducer:
     def _launch(self, b):
         self._launched[b] = True
         if self.world > 1:
-            self._works.append(dist.all_reduce(self.buckets[b], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+            op = dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
+            self._works.append(dist.all_reduce(self.buckets[b], op=op, group=self.pg, async_op=True))
 
     def finish(self):
         """call after backward, before the optimizer step"""
@@ -92,22 +98,44 @@ class GradReducer:
         for w in self._works:
             w.wait()
         self._works = []
-        if self.world > 1:
-            inv = 1.0 / self.world
-            for flat in self.buckets:
-                flat.mul_(inv)
+        if self.world > 1 and not self._avg:
+            self.arena.mul_(1.0 / self.world)
 
     def allreduce_all(self):
         """un-overlapped exchange of every bucket (used between the two CUDA graphs of a graphed step, where the
         per-parameter hooks do not run): all buckets are enqueued back to back, then awaited and averaged"""
         if self.world <= 1:
             return
-        works = [dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.pg, async_op=True) for flat in self.buckets]
-        for w in works:
-            w.wait()
-        inv = 1.0 / self.world
-        for flat in self.buckets:
-            flat.mul_(inv)
+        if self._avg:
+            dist.all_reduce(self.arena, op=dist.ReduceOp.AVG, group=self.pg)
+        else:
+            dist.all_reduce(self.arena, op=dist.ReduceOp.SUM, group=self.pg)
+            self.arena.mul_(1.0 / self.world)
+
+    def range_of(self, params):
+        """[lo, hi) slice of the arena holding exactly the gradients of `params` (which must be a prefix or a suffix of
+        the reducer's reverse-execution parameter order)"""
+        ids = {id(p) for p in params}
+        lo, hi, off = None, None, 0
+        for p in self.params:
+            n = (p.numel() + 7) // 8 * 8
+            if id(p) in ids:
+                lo = off if lo is None else lo
+                hi = off + n
+            off += n
+        inside = sum((p.numel() + 7) // 8 * 8 for p in self.params if id(p) in ids)
+        assert lo is not None and hi - lo == inside, 'parameters are not contiguous in the gradient arena'
+        return lo, hi
+
+    def allreduce_range(self, lo, hi, async_op=False):
+        if self.world <= 1:
+            return None
+        op = dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
+        w = dist.all_reduce(self.arena[lo:hi], op=op, group=self.pg, async_op=async_op)
+        if not self._avg:
+            assert not async_op, 'SUM + scale needs the synchronous path'
+            self.arena[lo:hi].mul_(1.0 / self.world)
+        return w
 
     def remove(self):
         for h in self._hooks:

@@ -49,6 +49,19 @@ def validation_step(model, videos, target):
     return output, scene_output, loss, acc1, acc5
 
 
+class _TapFn(torch.autograd.Function):
+    """identity whose output can be given to autograd.backward(inputs=...) as a cut point: the engine executes this
+    (free) node to fill .grad, but not the producer of its input"""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
 class GraphedTrainStep:
     """The whole training step (student forward, TrainLoss, backward, gradient exchange, optimizer update) captured once
     into a CUDA graph and replayed: the ~2000 kernel launches of a step cost one graph launch, which removes the host
@@ -59,40 +72,61 @@ class GraphedTrainStep:
     The optimizer must be capture-safe (e.g. torch.optim.AdamW(fused=True, capturable=True)).
     """
 
-    def __init__(self, model, train_criterion, optimizer, batches, reducer=None, warmup=3):
+    def __init__(self, model, train_criterion, optimizer, batches, reducer=None, warmup=3, split_block=3):
         self.model, self.crit, self.opt, self.reducer = model, train_criterion, optimizer, reducer
         self.batches = list(batches)
-        # With a reducer the step is split into two graphs around an eager NCCL exchange of the flat gradient buckets:
-        #   graph A: forward + loss + backward (gradients accumulate straight into the buckets; hooks are python and do not
-        #            run on replay, so the per-bucket overlap is traded for ~2000 fewer launches per step)
-        #   eager  : all-reduce of the buckets (NCCL over NVLink), 1/world
-        #   graph B: optimizer update + bucket memsets
+        # With a reducer the step becomes three graphs around the NCCL exchange of the flat gradient arena:
+        #   graph A1: forward + loss + backward down to the input of encoder block `split_block`
+        #   eager   : all-reduce of the gradients produced so far (head, slots, blocks >= split_block) -- asynchronous, it
+        #             overlaps graph A2 on the NCCL stream
+        #   graph A2: backward of blocks < split_block and the patch embedding
+        #   eager   : all-reduce of the remaining gradients
+        #   graph B : optimizer update + arena memset
+        # (per-parameter hooks are python and do not run on replay; NCCL inside a captured graph dead-locked here.)
         self.split = reducer is not None
+        self._tap = None
         if self.split:
             reducer.enabled = False
+            blocks = list(model.blocks)
+            split_block = max(1, min(split_block, len(blocks) - 1))
+            lower = [p for p in model.patch_embed.parameters()] + [p for b in blocks[:split_block] for p in b.parameters()]
+            lower = [p for p in lower if p.requires_grad]
+            low_ids = {id(p) for p in lower}
+            self.lower = lower
+            self.upper = [p for p in reducer.params if id(p) not in low_ids]
+            self.lo_range = reducer.range_of(lower)
+            self.up_range = reducer.range_of(self.upper)
+            self._hook = blocks[split_block].register_forward_pre_hook(self._grab)
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
         side.wait_stream(cur)
         with torch.cuda.stream(side):                      # warm-up off the capture stream (allocator, lazy inits)
             for i in range(warmup):
-                self._fwd_bwd(self.batches[i % len(self.batches)])
-                self._exchange()
+                self._fwd_bwd1(self.batches[i % len(self.batches)])
+                self._bwd2()
+                self._exchange_all()
                 self._update()
         cur.wait_stream(side)
         torch.cuda.synchronize()
-        self.graphs, self.losses = [], []
+        self.graphs, self.graphs2, self.losses = [], [], []
         pool = None
         from . import _lib
         for b in self.batches:
             g = torch.cuda.CUDAGraph()
             n0 = _lib.launch_count()
             with torch.cuda.graph(g, pool=pool):
-                loss = self._fwd_bwd(b)
+                loss = self._fwd_bwd1(b)
                 if not self.split:
                     self.opt.step()
-            self.launches_per_step = _lib.launch_count() - n0
             pool = g.pool()
+            g2 = None
+            if self.split:
+                g2 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g2, pool=pool):
+                    self._bwd2()
+            self.launches_per_step = _lib.launch_count() - n0
             self.graphs.append(g)
+            self.graphs2.append(g2)
             self.losses.append(loss)
             if not self.split:
                 self.opt.zero_grad(set_to_none=True)
@@ -102,13 +136,31 @@ class GraphedTrainStep:
             with torch.cuda.graph(self.update_graph, pool=pool):
                 self._update()
 
-    def _fwd_bwd(self, b):
+    def _grab(self, module, args):
+        x = args[0]
+        if torch.is_grad_enabled() and x.requires_grad:
+            y = _TapFn.apply(x)
+            y.retain_grad()
+            self._tap = (x, y)
+            return (y,) + tuple(args[1:])
+        return None
+
+    def _fwd_bwd1(self, b):
         loss, _, _ = train_class_batch(self.model, None, b['clip'], b['target'], self.crit, (b['fg'], b['fgf']),
                                        teacher_logits=b['teacher'])
-        loss.backward()
+        if self.split:
+            torch.autograd.backward([loss], inputs=self.upper + [self._tap[1]], retain_graph=True)
+        else:
+            loss.backward()
         return loss.detach()
 
-    def _exchange(self):
+    def _bwd2(self):
+        if self.split:
+            (x_pre, x_post), self._tap = self._tap, None
+            torch.autograd.backward([x_pre], [x_post.grad], inputs=self.lower)
+            x_post.grad = None
+
+    def _exchange_all(self):
         if self.split:
             self.reducer.allreduce_all()
 
@@ -123,6 +175,10 @@ class GraphedTrainStep:
         """replay the step on static batch `index`; returns the (static) loss tensor of that graph"""
         self.graphs[index].replay()
         if self.split:
-            self.reducer.allreduce_all()
+            w = self.reducer.allreduce_range(*self.up_range, async_op=self.reducer._avg)
+            self.graphs2[index].replay()
+            if w is not None:
+                w.wait()
+            self.reducer.allreduce_range(*self.lo_range)
             self.update_graph.replay()
         return self.losses[index]
