@@ -28,7 +28,8 @@ def token_stats(tokens: torch.Tensor, eps: float = 1e-5):
 
 
 def slot_stream_torch(tokens, mu, r, g, G, c0):
-    """INTERIM torch evaluation of the streaming step (same contract as the CUDA kernel):
+    """torch evaluation of the streaming step on the GPU (same contract as the CUDA kernels; used to differentiate the
+    S = 8 micro-benchmark configuration, whose backward kernel is not instantiated, and by the kernel tests):
     tokens [B,N,D]; mu,r [B,N]; g [B,HS,D]; G,c0 [B,HS]  ->  U [B,HS,D], m [B,HS], A [B,HS], a [B,HS,N]"""
     t = tokens if tokens.dtype == torch.float64 else tokens.float()
     B, HS, D = g.shape
