@@ -85,7 +85,7 @@ class AggregationBlock(nn.Module):
                     wo=a.to_out[0].weight, bo=a.to_out[0].bias)
 
     def _forward_streaming(self, data):
-        from .. import slot_kernels
+        from .. import slot_kernels, slot_linear
         with torch.autocast('cuda', enabled=False):
             x = self.get_queries(data.shape[0]).float()
             mu, r = slot_kernels.token_stats(data)
@@ -93,9 +93,11 @@ class AggregationBlock(nn.Module):
             sim = None
             for cross_attn, _, cross_ff, _ in self.layers:
                 attn, sim = SA.slot_attention_layer(x, data, mu, r, self._layer_params(cross_attn),
-                                                    stream=slot_kernels.slot_stream, sink=sink)
+                                                    stream=slot_kernels.slot_stream, lin=slot_linear, sink=sink)
                 x = attn + x
-                x = cross_ff(x) + x
+                net = cross_ff.fn.net                            # PreNorm(FeedForward): Linear, GELU, Dropout(0), Linear
+                h = slot_linear.linear(cross_ff.norm(x), net[0].weight, net[0].bias)
+                x = slot_linear.linear(net[1](h), net[3].weight, net[3].bias) + x
             return self.last_layer(x), sim
 
     def forward(self, data):

@@ -1,0 +1,276 @@
+// Slot-side linear algebra (fp32): products whose row count is M = clips x slots (a few dozen) against the aggregation
+// block's and the heads' weights -- agg_block/attention.py:120-141 (to_q, the folded to_k / to_v, to_out), :81-82
+// (FeedForward), model/modeling_slot.py:390-410 (head, mask predictor) and their gradients.  With so few rows every
+// product is bound by reading (or, for the weight gradients, writing) the weight matrix once, so the three kernels
+// below are organised around one coalesced pass over the weights; the M rows live in shared memory / registers.
+//
+//   nt    : y[m, n]  = sum_k x[m, k] w[n, k] (+ bias[n])          weights [N, K]  (nn.Linear forward)
+//   nn    : y[m, n] += sum_k x[m, k] w[k, n]                      weights [K, N]  (input gradient; folded key projection)
+//   outer : c[i, j]  = sum_m a[m, i] b[m, j],  colsum[i] = sum_m a[m, i]          (weight / bias gradients)
+//
+// Rows of x / y / a / b are addressed through a two-level map  off(m) = (m / inner) * outer + (m % inner) * ld  plus a
+// per-problem (head) offset, which expresses the '(b s) (h d)' <-> 'b h s c' views of the folded attention without copies.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace dv {
+
+struct RowMap {
+  long long outer, ld, batch;
+  int inner;
+  __device__ __forceinline__ long long off(int m, int z) const {
+    return (long long)(m / inner) * outer + (long long)(m % inner) * ld + (long long)z * batch;
+  }
+};
+
+constexpr int kSkMT = 16;          // rows per pass
+constexpr int kSkKC = 1024;        // K chunk held in shared memory (64 KiB)
+constexpr int kSkWR = kSkKC / 128; // weight float4s per lane, column and chunk
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+  const int n = valid ? 16 : 0;    // src-size 0: the 16 bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------------- nt
+// One warp <-> two weight rows (output columns); the lanes stride K with 16-byte loads.  Per K chunk the warp's weight
+// slice goes to registers and the x tile to shared memory (cp.async), both in flight together: one L2 round trip per chunk.
+__global__ void __launch_bounds__(256) skinny_nt_kernel(const float* __restrict__ x, RowMap xm, const float* __restrict__ w,
+                                                        long long w_batch, const float* __restrict__ bias, float* __restrict__ y,
+                                                        RowMap ym, int M, int N, int K) {
+  extern __shared__ float4 xs4[];                                  // [16][kc / 4]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nthreads = blockDim.x;
+  const int z = blockIdx.z, m0 = blockIdx.y * kSkMT;
+  const int n0 = blockIdx.x * (nthreads >> 4) + warp * 2;
+  const float* wz = w + (long long)z * w_batch;
+  const float4* w0 = reinterpret_cast<const float4*>(wz + (long long)min(n0, N - 1) * K);
+  const float4* w1 = reinterpret_cast<const float4*>(wz + (long long)min(n0 + 1, N - 1) * K);
+  const uint32_t xs_u = smem_u32(xs4);
+  float acc[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += kSkKC) {
+    const int kc4 = min(kSkKC, K - k0) >> 2;
+    __syncthreads();                                               // the previous chunk's x tile is no longer read
+    float4 wa[kSkWR], wb[kSkWR];
+#pragma unroll
+    for (int q = 0; q < kSkWR; ++q) {
+      const int c = lane + 32 * q;
+      const bool ok = c < kc4;
+      wa[q] = ok ? __ldg(w0 + (k0 >> 2) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      wb[q] = ok ? __ldg(w1 + (k0 >> 2) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int m = warp; m < kSkMT; m += (nthreads >> 5)) {
+      const bool ok = m0 + m < M;
+      const float4* src = reinterpret_cast<const float4*>(x + xm.off(ok ? m0 + m : m0, z) + k0);
+      for (int c = lane; c < kc4; c += 32) cp_async16(xs_u + (m * kc4 + c) * 16, src + c, ok);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < kSkWR; ++q) {
+      const int c = lane + 32 * q;
+      if (c < kc4) {
+#pragma unroll
+        for (int m = 0; m < kSkMT; ++m) {
+          const float4 v = xs4[m * kc4 + c];
+          acc[m] = fmaf(v.x, wa[q].x, fmaf(v.y, wa[q].y, fmaf(v.z, wa[q].z, fmaf(v.w, wa[q].w, acc[m]))));
+          acc[16 + m] = fmaf(v.x, wb[q].x, fmaf(v.y, wb[q].y, fmaf(v.z, wb[q].z, fmaf(v.w, wb[q].w, acc[16 + m]))));
+        }
+      }
+    }
+  }
+  // butterfly: 31 shuffles leave in lane l the warp total of acc[l]  (l = column * 16 + row)
+#pragma unroll
+  for (int off = 16, n = 32; off >= 1; off >>= 1, n >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      const float lo = acc[i], hi = acc[i + n / 2];
+      const float other = __shfl_xor_sync(0xffffffffu, up ? lo : hi, off);
+      acc[i] = (up ? hi : lo) + other;
+    }
+  }
+  const int m = m0 + (lane & 15), n = n0 + (lane >> 4);
+  if (m < M && n < N) y[ym.off(m, z) + n] = acc[0] + (bias != nullptr ? __ldg(bias + n) : 0.f);
+}
+
+// ---------------------------------------------------------------------------------------------------------------- nn
+constexpr int kSkNnThreads = 128;  // one output column per thread
+constexpr int kSkNnKS = 64;        // k rows per CTA
+
+__global__ void __launch_bounds__(kSkNnThreads) skinny_nn_kernel(const float* __restrict__ x, RowMap xm, const float* __restrict__ w,
+                                                                 long long w_batch, float* __restrict__ y, RowMap ym, int M,
+                                                                 int N, int K, int mtiles) {
+  __shared__ float4 xs4[kSkMT * kSkNnKS / 4];                      // [16][64 k], zero-padded (K may be any size: C + 365 logits)
+  const int tid = threadIdx.x;
+  const int z = blockIdx.z / mtiles, m0 = (blockIdx.z % mtiles) * kSkMT;
+  const int k0 = blockIdx.y * kSkNnKS, ks = min(kSkNnKS, K - k0);
+  const int n = blockIdx.x * kSkNnThreads + tid;
+  const float* wp = w + (long long)z * w_batch + (long long)k0 * N + min(n, N - 1);
+  float bw[kSkNnKS / 2];
+#pragma unroll
+  for (int q = 0; q < kSkNnKS / 2; ++q) bw[q] = (q < ks) ? __ldg(wp + (long long)q * N) : 0.f;    // first half: in flight with x
+  {
+    float xv[kSkMT * kSkNnKS / kSkNnThreads];
+#pragma unroll
+    for (int j = 0; j < kSkMT * kSkNnKS / kSkNnThreads; ++j) {
+      const int i = tid + j * kSkNnThreads, m = i / kSkNnKS, k = i % kSkNnKS;
+      xv[j] = (m0 + m < M && k < ks) ? __ldg(x + xm.off(m0 + m, z) + k0 + k) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < kSkMT * kSkNnKS / kSkNnThreads; ++j) reinterpret_cast<float*>(xs4)[tid + j * kSkNnThreads] = xv[j];
+  }
+  __syncthreads();
+  float acc[kSkMT];
+#pragma unroll
+  for (int m = 0; m < kSkMT; ++m) acc[m] = 0.f;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    float bn[kSkNnKS / 2];
+    if (half == 0) {
+#pragma unroll
+      for (int q = 0; q < kSkNnKS / 2; ++q) bn[q] = (kSkNnKS / 2 + q < ks) ? __ldg(wp + (long long)(kSkNnKS / 2 + q) * N) : 0.f;
+    }
+#pragma unroll
+    for (int c = 0; c < kSkNnKS / 8; ++c) {
+#pragma unroll
+      for (int m = 0; m < kSkMT; ++m) {
+        const float4 v = xs4[m * (kSkNnKS / 4) + half * (kSkNnKS / 8) + c];
+        acc[m] = fmaf(v.x, bw[4 * c], fmaf(v.y, bw[4 * c + 1], fmaf(v.z, bw[4 * c + 2], fmaf(v.w, bw[4 * c + 3], acc[m]))));
+      }
+    }
+    if (half == 0) {
+#pragma unroll
+      for (int q = 0; q < kSkNnKS / 2; ++q) bw[q] = bn[q];
+    }
+  }
+  if (n >= N) return;
+#pragma unroll
+  for (int m = 0; m < kSkMT; ++m)
+    if (m0 + m < M) atomicAdd(y + ym.off(m0 + m, z) + n, acc[m]);
+}
+
+// ------------------------------------------------------------------------------------------------------------- outer
+constexpr int kSkOutRows = 8;      // rows i of c per CTA
+
+__global__ void __launch_bounds__(256) skinny_outer_kernel(const float* __restrict__ a, RowMap am, const float* __restrict__ b, RowMap bm,
+                                                           float* __restrict__ c, long long c_batch, float* __restrict__ colsum,
+                                                           long long colsum_batch, int M, int I, int J) {
+  __shared__ float4 as4[kSkOutRows * kSkMT / 4];                   // [8 rows i][16 m]
+  const int tid = threadIdx.x, z = blockIdx.z;
+  const int i0 = blockIdx.y * kSkOutRows;
+  const int j4 = blockIdx.x * blockDim.x + tid;                    // float4 column of b / c
+  const bool active = 4 * j4 < J;
+  float4 acc[kSkOutRows];
+#pragma unroll
+  for (int i = 0; i < kSkOutRows; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float cs = 0.f;
+  for (int m0 = 0; m0 < M; m0 += kSkMT) {
+    float4 bv[kSkMT];                                              // issued first: in flight together with the a tile
+#pragma unroll
+    for (int mm = 0; mm < kSkMT; ++mm)
+      bv[mm] = (active && m0 + mm < M) ? __ldg(reinterpret_cast<const float4*>(b + bm.off(m0 + mm, z)) + j4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+    for (int t = tid; t < kSkOutRows * kSkMT; t += blockDim.x) {
+      const int i = t & (kSkOutRows - 1), m = t / kSkOutRows;      // consecutive threads <-> consecutive i: coalesced
+      const float v = (m0 + m < M && i0 + i < I) ? __ldg(a + am.off(m0 + m, z) + i0 + i) : 0.f;
+      reinterpret_cast<float*>(as4)[i * kSkMT + m] = v;
+    }
+    __syncthreads();
+    if (colsum != nullptr && blockIdx.x == 0 && tid < kSkOutRows) {
+#pragma unroll
+      for (int q = 0; q < kSkMT / 4; ++q) {
+        const float4 v = as4[tid * (kSkMT / 4) + q];
+        cs += (v.x + v.y) + (v.z + v.w);
+      }
+    }
+    if (active) {
+#pragma unroll
+      for (int q = 0; q < kSkMT / 4; ++q) {
+#pragma unroll
+        for (int i = 0; i < kSkOutRows; ++i) {
+          const float4 av = as4[i * (kSkMT / 4) + q];
+          const float4 b0 = bv[4 * q], b1 = bv[4 * q + 1], b2 = bv[4 * q + 2], b3 = bv[4 * q + 3];
+          acc[i].x = fmaf(av.x, b0.x, fmaf(av.y, b1.x, fmaf(av.z, b2.x, fmaf(av.w, b3.x, acc[i].x))));
+          acc[i].y = fmaf(av.x, b0.y, fmaf(av.y, b1.y, fmaf(av.z, b2.y, fmaf(av.w, b3.y, acc[i].y))));
+          acc[i].z = fmaf(av.x, b0.z, fmaf(av.y, b1.z, fmaf(av.z, b2.z, fmaf(av.w, b3.z, acc[i].z))));
+          acc[i].w = fmaf(av.x, b0.w, fmaf(av.y, b1.w, fmaf(av.z, b2.w, fmaf(av.w, b3.w, acc[i].w))));
+        }
+      }
+    }
+  }
+  if (active) {
+    float* cz = c + (long long)z * c_batch;
+#pragma unroll
+    for (int i = 0; i < kSkOutRows; ++i)
+      if (i0 + i < I) reinterpret_cast<float4*>(cz + (long long)(i0 + i) * J)[j4] = acc[i];
+  }
+  if (colsum != nullptr && blockIdx.x == 0 && tid < kSkOutRows && i0 + tid < I) colsum[(long long)z * colsum_batch + i0 + tid] = cs;
+}
+
+static RowMap make_map(const int64_t* m) {
+  RowMap r;
+  r.outer = m[0]; r.inner = (int)m[1]; r.ld = m[2]; r.batch = m[3];
+  return r;
+}
+static bool map_ok(const int64_t* m) { return m != nullptr && m[1] > 0 && m[0] % 4 == 0 && m[2] % 4 == 0 && m[3] % 4 == 0; }
+
+}  // namespace dv
+
+using namespace dv;
+
+extern "C" int devias_skinny_nt(const float* x, const int64_t* x_map, const float* w, int64_t w_batch, const float* bias, float* y,
+                                const int64_t* y_map, int M, int N, int K, int batch, void* stream) {
+  DV_REQUIRE(x && w && y, "null pointer");
+  DV_REQUIRE(M > 0 && N > 0 && K > 0 && batch > 0 && K % 4 == 0, "skinny_nt: K must be a multiple of 4");
+  DV_REQUIRE(map_ok(x_map) && y_map && y_map[1] > 0 && w_batch % 4 == 0, "skinny_nt: row maps must keep 16-byte alignment");
+  DV_REQUIRE((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w)) % 16 == 0, "skinny_nt: x / w must be 16-byte aligned");
+  static bool attr = false;
+  if (!attr) {
+    DV_CHECK_CUDA(cudaFuncSetAttribute(skinny_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSkMT * kSkKC * 4));
+    attr = true;
+  }
+  // 16 output columns per CTA (8 warps) when that still fills the GPU, else 8 (4 warps)
+  const int threads = ((long long)((N + 15) / 16) * ((M + kSkMT - 1) / kSkMT) * batch >= sm_count()) ? 256 : 128;
+  const int cols = threads >> 4;
+  const dim3 grid((N + cols - 1) / cols, (M + kSkMT - 1) / kSkMT, batch);
+  const size_t smem = (size_t)kSkMT * (K < kSkKC ? K : kSkKC) * 4;
+  skinny_nt_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(x, make_map(x_map), w, w_batch, bias, y, make_map(y_map), M, N, K);
+  DV_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return DEVIAS_OK;
+}
+
+extern "C" int devias_skinny_nn(const float* x, const int64_t* x_map, const float* w, int64_t w_batch, float* y, const int64_t* y_map,
+                                int M, int N, int K, int batch, void* stream) {
+  DV_REQUIRE(x && w && y, "null pointer");
+  DV_REQUIRE(M > 0 && N > 0 && K > 0 && batch > 0, "skinny_nn: empty problem");
+  DV_REQUIRE(x_map && x_map[1] > 0 && y_map && y_map[1] > 0, "skinny_nn: row maps need inner > 0");
+  const int mtiles = (M + kSkMT - 1) / kSkMT;
+  const dim3 grid((N + kSkNnThreads - 1) / kSkNnThreads, (K + kSkNnKS - 1) / kSkNnKS, batch * mtiles);
+  skinny_nn_kernel<<<grid, kSkNnThreads, 0, (cudaStream_t)stream>>>(x, make_map(x_map), w, w_batch, y, make_map(y_map), M, N, K, mtiles);
+  DV_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return DEVIAS_OK;
+}
+
+extern "C" int devias_skinny_outer(const float* a, const int64_t* a_map, const float* b, const int64_t* b_map, float* c,
+                                   int64_t c_batch, float* colsum, int64_t colsum_batch, int M, int I, int J, int batch,
+                                   void* stream) {
+  DV_REQUIRE(a && b && c, "null pointer");
+  DV_REQUIRE(M > 0 && I > 0 && J > 0 && batch > 0 && J % 4 == 0, "skinny_outer: J must be a multiple of 4");
+  DV_REQUIRE(a_map && a_map[1] > 0 && map_ok(b_map) && c_batch % 4 == 0, "skinny_outer: row maps must keep 16-byte alignment");
+  DV_REQUIRE((reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c)) % 16 == 0, "skinny_outer: b / c must be 16-byte aligned");
+  const int j4 = J / 4;
+  const int threads = j4 >= 256 ? 256 : (j4 + 31) / 32 * 32;
+  const dim3 grid((j4 + threads - 1) / threads, (I + kSkOutRows - 1) / kSkOutRows, batch);
+  skinny_outer_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(a, make_map(a_map), b, make_map(b_map), c, c_batch, colsum,
+                                                                 colsum_batch, M, I, J);
+  DV_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return DEVIAS_OK;
+}

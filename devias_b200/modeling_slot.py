@@ -194,7 +194,14 @@ class MaskPredictor(nn.Module):
         self.act = nn.ReLU()
 
     def forward(self, cls_token):
-        mask = self.decoder(cls_token)
+        if cls_token.is_cuda and cls_token.dtype == torch.float32:
+            from . import slot_linear
+            d = self.decoder
+            h = F.relu(slot_linear.linear(cls_token, d[0].weight, d[0].bias))
+            h = F.relu(slot_linear.linear(h, d[2].weight, d[2].bias))
+            mask = torch.sigmoid(slot_linear.linear(h, d[4].weight, d[4].bias))
+        else:
+            mask = self.decoder(cls_token)
         return mask.squeeze().reshape(cls_token.shape[0], 14 * 14)
 
 
@@ -368,6 +375,12 @@ class VisionTransformer(nn.Module):
                 x = blk(x, w16=w16)
             return LayerNormFn.apply(x, self.norm.weight, self.norm.bias, self.norm.eps, self.token_dtype)
 
+    def _head_linear(self, x):
+        if isinstance(self.head, nn.Linear) and x.dtype == torch.float32:
+            from . import slot_linear
+            return slot_linear.linear(x, self.head.weight, self.head.bias)
+        return self.head(x)
+
     def forward(self, x, return_attn=False):
         x = self.forward_features(x, return_attn)
         slots, attn = self.agg_block(x)
@@ -379,7 +392,7 @@ class VisionTransformer(nn.Module):
                 return (action_feat, scene_feat), (action_logit, scene_logit, []), ([], [], [])
             bs, num_slots, _ = slots.size()
             slots = slots.reshape(-1, 768)
-            slots_head = self.head(self.fc_dropout(slots))
+            slots_head = self._head_linear(self.fc_dropout(slots))
             probs = F.softmax(slots_head, dim=-1).view(bs, num_slots, -1)
             C = self.num_classes
             a_idx = torch.argmax(probs[:, :, :C].max(dim=-1).values, dim=1)

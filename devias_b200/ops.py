@@ -142,6 +142,59 @@ def patchify(clip: torch.Tensor):
     return out
 
 
+def _rowmap(outer, inner, ld, batch):
+    import ctypes
+    return (ctypes.c_int64 * 4)(int(outer), int(inner), int(ld), int(batch))
+
+
+def rowmap(view: torch.Tensor):
+    """Row map of a [Z, M, C] or [Z, M1, M2, C] strided VIEW (unit stride on C): problem z, row m = m1 * M2 + m2."""
+    assert view.stride(-1) == 1 or view.shape[-1] == 1
+    if view.dim() == 3:
+        return _rowmap(0, max(view.shape[1], 1), view.stride(1), view.stride(0))
+    assert view.dim() == 4
+    return _rowmap(view.stride(1), view.shape[2], view.stride(2), view.stride(0))
+
+
+def skinny_nt(x: torch.Tensor, w: torch.Tensor, bias, y: torch.Tensor):
+    """y[z, m, :] = x[z, m, :] @ w[z].T (+ bias);  x, y: fp32 strided views [Z, M.., K] / [Z, M.., N]; w [Z, N, K] contiguous"""
+    _need_cuda(x)
+    Z, N, K = w.shape
+    M = x.numel() // (Z * K)
+    assert x.dtype == w.dtype == y.dtype == torch.float32 and w.is_contiguous() and x.shape[-1] == K and y.shape[-1] == N
+    assert y.numel() == Z * M * N and x.shape[0] == Z and y.shape[0] == Z
+    rc = _lib.lib().devias_skinny_nt(x.data_ptr(), rowmap(x), w.data_ptr(), N * K, _ptr(bias), y.data_ptr(), rowmap(y), M, N, K, Z,
+                                     _stream())
+    _lib.check(rc, 'skinny_nt')
+    return y
+
+
+def skinny_nn(x: torch.Tensor, w: torch.Tensor, y: torch.Tensor):
+    """y[z, m, :] += x[z, m, :] @ w[z];  w [Z, K, N] contiguous; y must be pre-filled"""
+    _need_cuda(x)
+    Z, K, N = w.shape
+    M = x.numel() // (Z * K)
+    assert x.dtype == w.dtype == y.dtype == torch.float32 and w.is_contiguous() and x.shape[-1] == K and y.shape[-1] == N
+    assert y.numel() == Z * M * N and x.shape[0] == Z and y.shape[0] == Z
+    rc = _lib.lib().devias_skinny_nn(x.data_ptr(), rowmap(x), w.data_ptr(), K * N, y.data_ptr(), rowmap(y), M, N, K, Z, _stream())
+    _lib.check(rc, 'skinny_nn')
+    return y
+
+
+def skinny_outer(a: torch.Tensor, b: torch.Tensor, want_colsum=False):
+    """c[z] = a[z].T @ b[z]  ([Z, I, J]);  optionally colsum[z, i] = sum_m a[z, m, i]"""
+    _need_cuda(a)
+    Z, I, J = a.shape[0], a.shape[-1], b.shape[-1]
+    M = a.numel() // (Z * I)
+    assert a.dtype == b.dtype == torch.float32 and b.shape[0] == Z and b.numel() == Z * M * J
+    c = torch.empty(Z, I, J, device=a.device, dtype=torch.float32)
+    cs = torch.empty(Z, I, device=a.device, dtype=torch.float32) if want_colsum else None
+    rc = _lib.lib().devias_skinny_outer(a.data_ptr(), rowmap(a), b.data_ptr(), rowmap(b), c.data_ptr(), I * J, _ptr(cs), I, M, I, J, Z,
+                                        _stream())
+    _lib.check(rc, 'skinny_outer')
+    return c, cs
+
+
 def flash_attn_fwd(qkv: torch.Tensor, B: int, N: int, H: int, need_lse=True):
     """qkv bf16 [B*N, 3*H*64] -> (out bf16 [B*N, H*64], lse2 fp32 [B, H, Npad] | None)"""
     _need_cuda(qkv)

@@ -44,20 +44,28 @@ def slot_stream_torch(tokens, mu, r, g, G, c0):
     return U, m, A, a
 
 
-def slot_attention_layer(x, tokens, mu, r, p, stream=slot_stream_torch, **stream_kw):
+def slot_attention_layer(x, tokens, mu, r, p, stream=slot_stream_torch, lin=None, **stream_kw):
     """One `PreNorm(Attention)` application on slots x [B,S,D] against tokens [B,N,D].
     p: dict with norm_w/b (slots LN), ctx_w/b (context LN), wq, wk, wv [2048,768], wo [768,2048], bo.
+    lin: provider of the slot-row products (devias_b200.slot_linear on CUDA; torch expressions when None).
     Returns (to_out(attn.v) [B,S,D], sim_distill [(B*4), S, N])."""
     B, S, D = x.shape
     H = HEADS
     dh = p['wq'].shape[0] // H
+    linear = F.linear if lin is None else lin.linear
     xn = F.layer_norm(x, (D,), p['norm_w'], p['norm_b'], 1e-5)
-    q = F.linear(xn, p['wq']).view(B, S, H, dh)
-    qt = torch.einsum('bshd,hdc->bhsc', q, p['wk'].view(H, dh, D)) * (dh ** -0.5)     # [B,H,S,D]
+    q = linear(xn, p['wq']).view(B, S, H, dh)
+    if lin is None:
+        qt = torch.einsum('bshd,hdc->bhsc', q, p['wk'].view(H, dh, D)) * (dh ** -0.5)     # [B,H,S,D]
+    else:
+        qt = lin.fold_keys(q, p['wk']) * (dh ** -0.5)
     g = (qt * p['ctx_w']).reshape(B, H * S, D)
     G = g.sum(-1)
     c0 = (qt @ p['ctx_b']).reshape(B, H * S)
     U, m, A, a = stream(tokens, mu, r, g.contiguous(), G.contiguous(), c0.contiguous(), **stream_kw)
     cbar = (p['ctx_w'] * (U - m.unsqueeze(-1)) + p['ctx_b'] * A.unsqueeze(-1)) / (A.unsqueeze(-1) + 1e-7)
-    out = torch.einsum('bhsc,hdc->bshd', cbar.view(B, H, S, D), p['wv'].view(H, dh, D)).reshape(B, S, H * dh)
-    return F.linear(out, p['wo'], p['bo']), a.reshape(B * H, S, -1)
+    if lin is None:
+        out = torch.einsum('bhsc,hdc->bshd', cbar.view(B, H, S, D), p['wv'].view(H, dh, D)).reshape(B, S, H * dh)
+    else:
+        out = lin.apply_values(cbar.view(B, H, S, D), p['wv'])
+    return linear(out, p['wo'], p['bo']), a.reshape(B * H, S, -1)

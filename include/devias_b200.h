@@ -130,6 +130,23 @@ int devias_scale_rows_cast(const float* in, void* out, int rows, int cols, const
 int devias_patchify(const void* clip, int clip_dtype, void* out, int batch, int chans, int frames, int height, int width,
                     void* stream);
 
+/* ---- slot-side products (fp32, M = clips x slots rows) -----------------------------------------------
+ * The aggregation block's projections and the heads act on B*S rows only (agg_block/attention.py:120-141 to_q / to_out
+ * and the folded to_k / to_v, :81-82 FeedForward; model/modeling_slot.py:390-410 head and mask predictor): every product
+ * is one pass over the weight matrix.  Rows of x / y / a / b are addressed by a map of four int64 (host memory)
+ *   {outer, inner, ld, batch}:  offset(m, z) = (m / inner) * outer + (m % inner) * ld + z * batch     (elements)
+ * and z = 0..batch-1 selects the problem (slot head); weights advance by w_batch per problem.
+ *   nt    : y[m, n]  = sum_k x[m, k] w[n, k] (+ bias[n])    w [N, K] row-major; K % 4 == 0
+ *   nn    : y[m, n] += sum_k x[m, k] w[k, n]                w [K, N] row-major; y is accumulated (caller pre-fills it)
+ *   outer : c[i, j]  = sum_m a[m, i] b[m, j]                c [I, J] row-major, J % 4 == 0; colsum[i] = sum_m a[m, i] if
+ *                                                           colsum != NULL (the bias gradient when a = dY) */
+int devias_skinny_nt(const float* x, const int64_t* x_map, const float* w, int64_t w_batch, const float* bias, float* y,
+                     const int64_t* y_map, int M, int N, int K, int batch, void* stream);
+int devias_skinny_nn(const float* x, const int64_t* x_map, const float* w, int64_t w_batch, float* y, const int64_t* y_map,
+                     int M, int N, int K, int batch, void* stream);
+int devias_skinny_outer(const float* a, const int64_t* a_map, const float* b, const int64_t* b_map, float* c, int64_t c_batch,
+                        float* colsum, int64_t colsum_batch, int M, int I, int J, int batch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,65 @@
+"""Slot-side products (csrc/skinny.cu through devias_b200.slot_linear) against torch fp32/fp64 on the same inputs."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
+
+
+@pytest.mark.parametrize('M,K,N,bias', [(16, 768, 3072, True), (16, 3072, 768, True), (4, 768, 2048, False), (16, 768, 466, True),
+                                        (32, 768, 765, True), (2, 256, 196, True), (37, 2048, 768, True)])
+def test_linear_matches_torch(M, K, N, bias):
+    from devias_b200 import slot_linear
+    g = torch.Generator(device='cuda').manual_seed(M * 7 + N)
+    x = torch.randn(M, K, device='cuda', generator=g, requires_grad=True)
+    w = (torch.randn(N, K, device='cuda', generator=g) * 0.05).requires_grad_(True)
+    b = torch.randn(N, device='cuda', generator=g).requires_grad_(True) if bias else None
+    dy = torch.randn(M, N, device='cuda', generator=g)
+    y = slot_linear.linear(x, w, b)
+    grads = torch.autograd.grad(y, [x, w] + ([b] if bias else []), dy)
+    xd, wd = x.detach().double().requires_grad_(True), w.detach().double().requires_grad_(True)
+    bd = b.detach().double().requires_grad_(True) if bias else None
+    yr = F.linear(xd, wd, bd)
+    gr = torch.autograd.grad(yr, [xd, wd] + ([bd] if bias else []), dy.double())
+    assert _rel(y, yr) < 2e-6
+    for a, r in zip(grads, gr):
+        assert a.shape == r.shape and _rel(a, r) < 2e-6
+
+
+def test_linear_3d_input_and_large_rows_fallback():
+    from devias_b200 import slot_linear
+    x = torch.randn(8, 2, 768, device='cuda')
+    w = torch.randn(512, 768, device='cuda') * 0.05
+    assert _rel(slot_linear.linear(x, w), F.linear(x.double(), w.double())) < 2e-6
+    xl = torch.randn(slot_linear.MAX_ROWS + 1, 768, device='cuda')
+    assert _rel(slot_linear.linear(xl, w), F.linear(xl.double(), w.double())) < 1e-5
+
+
+@pytest.mark.parametrize('B,S', [(8, 2), (1, 2), (3, 4), (32, 2), (5, 8)])
+def test_fold_keys_and_apply_values(B, S):
+    from devias_b200 import slot_linear
+    H, dh, D = 4, 512, 768
+    g = torch.Generator(device='cuda').manual_seed(B * 11 + S)
+    q = torch.randn(B, S, H, dh, device='cuda', generator=g, requires_grad=True)
+    wk = (torch.randn(H * dh, D, device='cuda', generator=g) * 0.05).requires_grad_(True)
+    dqt = torch.randn(B, H, S, D, device='cuda', generator=g)
+    qt = slot_linear.fold_keys(q, wk)
+    gq, gw = torch.autograd.grad(qt, [q, wk], dqt)
+    qd, wd = q.detach().double().requires_grad_(True), wk.detach().double().requires_grad_(True)
+    ref = torch.einsum('bshd,hdc->bhsc', qd, wd.view(H, dh, D))
+    rq, rw = torch.autograd.grad(ref, [qd, wd], dqt.double())
+    assert _rel(qt, ref) < 2e-6 and _rel(gq, rq) < 2e-6 and _rel(gw, rw) < 2e-6
+
+    cbar = torch.randn(B, H, S, D, device='cuda', generator=g, requires_grad=True)
+    wv = (torch.randn(H * dh, D, device='cuda', generator=g) * 0.05).requires_grad_(True)
+    dout = torch.randn(B, S, H * dh, device='cuda', generator=g)
+    out = slot_linear.apply_values(cbar, wv)
+    gc, gv = torch.autograd.grad(out, [cbar, wv], dout)
+    cd, vd = cbar.detach().double().requires_grad_(True), wv.detach().double().requires_grad_(True)
+    ref = torch.einsum('bhsc,hdc->bshd', cd, vd.view(H, dh, D)).reshape(B, S, H * dh)
+    rc, rv = torch.autograd.grad(ref, [cd, vd], dout.double())
+    assert _rel(out, ref) < 2e-6 and _rel(gc, rc) < 2e-6 and _rel(gv, rv) < 2e-6
