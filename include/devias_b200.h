@@ -129,6 +129,8 @@ int devias_scale_rows_cast(const float* in, void* out, int rows, int cols, const
                            void* stream);
 int devias_patchify(const void* clip, int clip_dtype, void* out, int batch, int chans, int frames, int height, int width,
                     void* stream);
+/* diagnostic: the bare TMA token stream of the slot kernels (same tensor map / ring / tile split, no arithmetic) */
+int devias_debug_token_stream(const float* tokens, int batch, int n_tokens, int stages, float* scratch, void* stream);
 
 /* ---- slot-side products (fp32, M = clips x slots rows) -----------------------------------------------
  * The aggregation block's projections and the heads act on B*S rows only (agg_block/attention.py:120-141 to_q / to_out
