@@ -822,10 +822,12 @@ struct SlotBwd2Cfg {
   static constexpr int STAGES = 3;
   static constexpr int NV = 12;                                       // gd[4], dU[8]
   static constexpr int OFF_TILE = 0;
-  static constexpr int OFF_VEC = STAGES * kSTileBytes;                // vec[12][768]
-  static constexpr int OFF_PART = OFF_VEC + NV * kSD * 4;             // partial[8 warps][16 tokens][12]
-  static constexpr int OFF_COEF = OFF_PART + WARPS * kST * NV * 4;    // coef[16 tokens][12]: alpha[4], beta[4], r, lambda, kappa, pad
-  static constexpr int OFF_BAR = OFF_COEF + kST * 12 * 4;
+  // two groups of four warps take alternate tiles (each runs all three phases of its tile, so the phases of one group
+  // fill the latencies of the other); vec / partial / coef exist once per group
+  static constexpr int OFF_VEC = STAGES * kSTileBytes;                // vec[2][12][768]
+  static constexpr int OFF_PART = OFF_VEC + 2 * NV * kSD * 4;         // partial[2][4 warps][16 tokens][12]
+  static constexpr int OFF_COEF = OFF_PART + 2 * 4 * kST * NV * 4;    // coef[2][16 tokens][12]: alpha[4], beta[4], r, lambda, kappa, pad
+  static constexpr int OFF_BAR = OFF_COEF + 2 * kST * 12 * 4;
   static constexpr int BYTES = OFF_BAR + 64 + 1024;
 };
 
@@ -843,9 +845,11 @@ slot_stream_bwd2_kernel(const __grid_constant__ CUtensorMap tmTok, const SlotBwd
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
-  const uint32_t vec_u = smem_u32(smem + Cfg::OFF_VEC), part_u = smem_u32(smem + Cfg::OFF_PART), coef_u = smem_u32(smem + Cfg::OFF_COEF);
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int grp = tid >> 7, tg = tid & 127, warp = (tid >> 5) & 3;     // group, thread and warp within the group
+  const uint32_t vec_u = smem_u32(smem + Cfg::OFF_VEC) + grp * (Cfg::NV * kSD * 4);
+  const uint32_t part_u = smem_u32(smem + Cfg::OFF_PART) + grp * (4 * kST * Cfg::NV * 4);
+  const uint32_t coef_u = smem_u32(smem + Cfg::OFF_COEF) + grp * (kST * 12 * 4);
   const int tpc = p.tiles_per_clip;
   const long long total = (long long)p.B * tpc;
   const int start = (int)(total * blockIdx.x / gridDim.x), end = (int)(total * (blockIdx.x + 1) / gridDim.x);
@@ -862,34 +866,34 @@ slot_stream_bwd2_kernel(const __grid_constant__ CUtensorMap tmTok, const SlotBwd
     tma_load_4d(smem + Cfg::OFF_TILE + st * kSTileBytes, &tmTok, &full[st], 0, (gt % tpc) * kST, 0, gt / tpc);
   };
   if (tid == 0) {
-    for (int it = 0; it < Cfg::STAGES - 1 && start + it < end; ++it) issue(it);
+    for (int it = 0; it < Cfg::STAGES && start + it < end; ++it) issue(it);
   }
 
-  // phase 1: lane <-> (token quad {tq, tq+4, tq+8, tq+12}, eighth e); a warp covers 24 of the 192 channel chunks
+  // phase 1: lane <-> (token quad {tq, tq+4, tq+8, tq+12}, eighth e); a warp covers 48 of the 192 channel chunks
   const int tq = lane & 3, e8 = lane >> 2;
   // after the butterfly the lane holds 6 of the quad's 48 sums: indices pbase .. pbase+5 (index = token_i * 12 + vector)
   const int pbase = ((lane >> 4) & 1) * 24 + ((lane >> 3) & 1) * 12 + ((lane >> 2) & 1) * 6;
   // phase 1b: thread <-> (token, head, slice); slice s sums the partials of warps 2s, 2s+1
-  const int tk1 = tid >> 4, h1 = (tid >> 2) & 3, sl1 = tid & 3;
-  // phase 2: thread <-> channel pairs 2u, 256 + 2u, 512 + 2u of the tokens [8 half, 8 half + 8)
-  const int u = tid & 127, half = tid >> 7;
+  const int tk1 = tg >> 3, h1 = (tg >> 1) & 3, sl1 = tg & 1;
+  // phase 2: thread <-> channel pairs 2u, 256 + 2u, 512 + 2u of all 16 tokens
+  const int u = tg;
   const int cchunk = u >> 1, cin = (u & 1) * 8;
 
-  for (int gt = start; gt < end;) {
+  for (int gt = start + grp; gt < end;) {
     const int b = gt / tpc;
     const int seg_end = min(end, (b + 1) * tpc);
-    __syncthreads();                                                 // previous clip: phase 2 and its register reads are done
+    named_bar_sync(1 + grp, 128);                                    // previous clip: phase 2 and its register reads are done
     {  // vec rows 0..3: gd[h] = g[h,1] - g[h,0];  rows 4..11: dU[h,s]
       const float4* sg = reinterpret_cast<const float4*>(p.g + (long long)b * HS * kSD);
       const float4* sd = reinterpret_cast<const float4*>(p.dU + (long long)b * HS * kSD);
-      for (int i = tid; i < 4 * (kSD / 4); i += Cfg::THREADS) {
+      for (int i = tg; i < 4 * (kSD / 4); i += 128) {
         const int h = i / (kSD / 4), c = i % (kSD / 4);
         const float4 a1 = __ldg(sg + (2 * h + 1) * (kSD / 4) + c), a0 = __ldg(sg + (2 * h) * (kSD / 4) + c);
         sts128f(vec_u + i * 16, make_float4(a1.x - a0.x, a1.y - a0.y, a1.z - a0.z, a1.w - a0.w));
       }
-      for (int i = tid; i < HS * (kSD / 4); i += Cfg::THREADS) sts128f(vec_u + (4 * (kSD / 4) + i) * 16, __ldg(sd + i));
+      for (int i = tg; i < HS * (kSD / 4); i += 128) sts128f(vec_u + (4 * (kSD / 4) + i) * 16, __ldg(sd + i));
     }
-    __syncthreads();
+    named_bar_sync(1 + grp, 128);
     uint64_t gd[4][3], dud[4][3], du0[3], dgacc[4][3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -925,16 +929,16 @@ slot_stream_bwd2_kernel(const __grid_constant__ CUtensorMap tmTok, const SlotBwd
     };
     fetch(gt);
 
-    for (; gt < seg_end; ++gt) {
+    for (; gt < seg_end; gt += 2) {
       const int it = gt - start, st = it % Cfg::STAGES;
       const int tok_base = (gt % tpc) * kST;
       const float a0 = n_a0, a1 = n_a1, mu = n_mu, r = n_r;
       float da0 = dA0 + n_d0, da1 = dA1 + n_d1;
-      fetch(gt + 1);
+      fetch(gt + 2);
 
       mbar_wait(&full[st], (it / Cfg::STAGES) & 1);
       const uint32_t tile = smem_u32(smem + Cfg::OFF_TILE + st * kSTileBytes);
-      // ---------------- phase 1: the 12 dot products of four tokens over this lane's 3 chunks
+      // ---------------- phase 1: the 12 dot products of four tokens over this lane's 6 chunks
       {
         uint64_t d[4][Cfg::NV];
 #pragma unroll
@@ -942,8 +946,8 @@ slot_stream_bwd2_kernel(const __grid_constant__ CUtensorMap tmTok, const SlotBwd
 #pragma unroll
           for (int v = 0; v < Cfg::NV; ++v) d[i][v] = 0ull;
 #pragma unroll 1
-        for (int c = 0; c < 3; ++c) {
-          const int c4 = warp * 24 + 8 * c + e8;
+        for (int c = 0; c < 6; ++c) {
+          const int c4 = warp * 48 + 8 * c + e8;
           uint64_t t01[4], t23[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -980,8 +984,7 @@ slot_stream_bwd2_kernel(const __grid_constant__ CUtensorMap tmTok, const SlotBwd
           sts32(part_u + ((warp * kST + tq + 4 * ti) * Cfg::NV + v) * 4, x[j]);
         }
       }
-      __syncthreads();                                               // partials visible; everyone is past phase 2 of the previous tile
-      if (tid == 0 && gt + Cfg::STAGES - 1 < end) issue(it + Cfg::STAGES - 1);
+      named_bar_sync(1 + grp, 128);                                  // partials of the group's four warps are visible
       // ---------------- phase 1b: per-token coefficients
       {
         float ed = 0.f, f0 = 0.f, f1 = 0.f;
@@ -993,7 +996,6 @@ slot_stream_bwd2_kernel(const __grid_constant__ CUtensorMap tmTok, const SlotBwd
           f0 += fv.x; f1 += fv.y;
         }
         ed += __shfl_xor_sync(0xffffffffu, ed, 1); f0 += __shfl_xor_sync(0xffffffffu, f0, 1); f1 += __shfl_xor_sync(0xffffffffu, f1, 1);
-        ed += __shfl_xor_sync(0xffffffffu, ed, 2); f0 += __shfl_xor_sync(0xffffffffu, f0, 2); f1 += __shfl_xor_sync(0xffffffffu, f1, 2);
         ed -= mu * (G1 - G0);                                        // e[h,1] - e[h,0]
         f0 = fmaf(mu, dm0, f0); f1 = fmaf(mu, dm1, f1);
         da0 = fmaf(r, f0, da0); da1 = fmaf(r, f1, da1);
@@ -1001,8 +1003,8 @@ slot_stream_bwd2_kernel(const __grid_constant__ CUtensorMap tmTok, const SlotBwd
         const float ds0 = a0 * (da0 - dot), ds1 = a1 * (da1 - dot);
         float dr = fmaf(ds1, ed, fmaf(a0, f0, a1 * f1));
         float dmu = fmaf(a0, dm0, a1 * dm1) - fmaf(ds0, G0, ds1 * G1);
+        dr += __shfl_xor_sync(0xffffffffu, dr, 2); dmu += __shfl_xor_sync(0xffffffffu, dmu, 2);
         dr += __shfl_xor_sync(0xffffffffu, dr, 4); dmu += __shfl_xor_sync(0xffffffffu, dmu, 4);
-        dr += __shfl_xor_sync(0xffffffffu, dr, 8); dmu += __shfl_xor_sync(0xffffffffu, dmu, 8);
         dmu *= r;
         const float lambda = -dr * r * r * r * (1.0f / kSD);
         const float kappa = dmu * (1.0f / kSD) - lambda * mu;
@@ -1016,12 +1018,12 @@ slot_stream_bwd2_kernel(const __grid_constant__ CUtensorMap tmTok, const SlotBwd
           accC0 += ds0; accC1 += ds1;
         }
       }
-      __syncthreads();
+      named_bar_sync(1 + grp, 128);
       // ---------------- phase 2: dt and the dg accumulators
       {
 #pragma unroll 2
-        for (int jj = 0; jj < 8; ++jj) {
-          const int j = half * 8 + jj, tok = tok_base + j;
+        for (int j = 0; j < kST; ++j) {
+          const int tok = tok_base + j;
           if (tok >= p.N) break;
           uint64_t t[3];
 #pragma unroll
@@ -1051,6 +1053,8 @@ slot_stream_bwd2_kernel(const __grid_constant__ CUtensorMap tmTok, const SlotBwd
           }
         }
       }
+      named_bar_sync(1 + grp, 128);                                  // the group is done with the stage: refill it (tile it + 3,
+      if (tg == 0 && gt + Cfg::STAGES < end) issue(it + Cfg::STAGES); // which the other group will consume)
     }
     // ---- flush this clip's share: dg[h,1] += acc, dg[h,0] -= acc; dG, dc0
     {
@@ -1064,10 +1068,12 @@ slot_stream_bwd2_kernel(const __grid_constant__ CUtensorMap tmTok, const SlotBwd
           red_add_v2_f32(dst + (2 * h) * kSD + 256 * k, -x, -y);
         }
       }
-      // the two tokens of a warp (lanes l, l ^ 16), then one atomic per (warp, head, slot)
+      // the four tokens of a warp (lanes l, l ^ 8, l ^ 16, l ^ 24), then one atomic per (warp, head, slot)
+      accG0 += __shfl_xor_sync(0xffffffffu, accG0, 8); accG1 += __shfl_xor_sync(0xffffffffu, accG1, 8);
+      accC0 += __shfl_xor_sync(0xffffffffu, accC0, 8); accC1 += __shfl_xor_sync(0xffffffffu, accC1, 8);
       accG0 += __shfl_xor_sync(0xffffffffu, accG0, 16); accG1 += __shfl_xor_sync(0xffffffffu, accG1, 16);
       accC0 += __shfl_xor_sync(0xffffffffu, accC0, 16); accC1 += __shfl_xor_sync(0xffffffffu, accC1, 16);
-      if (lane < 16 && sl1 == 0) {
+      if (lane < 8 && sl1 == 0) {
         atomicAdd(p.dG + b * HS + 2 * h1, accG0); atomicAdd(p.dG + b * HS + 2 * h1 + 1, accG1);
         atomicAdd(p.dc0 + b * HS + 2 * h1, accC0); atomicAdd(p.dc0 + b * HS + 2 * h1 + 1, accC1);
       }
