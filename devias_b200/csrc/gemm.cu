@@ -1,7 +1,10 @@
-// Persistent warp-specialised bf16 GEMM for sm_100a: TMA -> 128B-swizzled smem ring -> tcgen05.mma (cta_group::1,
-// 128 x BN x 16) -> fp32 accumulators double-buffered in tensor memory -> fused epilogue -> TMA store / TMA reduce-add.
-// CTAs run as clusters of two along M: the pair shares its B (weight) tile -- each CTA fetches half of it and TMA-multicasts
-// it into both shared memories.
+// Persistent warp-specialised bf16 GEMM for sm_100a: TMA -> 128B-swizzled smem ring -> tcgen05.mma.cta_group::2
+// (256 x BN x 16 over the two SMs of a cluster) -> fp32 accumulators double-buffered in tensor memory -> fused epilogue ->
+// TMA store / TMA reduce-add.  CTAs run as pairs along M: each CTA holds its own 128 rows of A and HALF of the B (weight)
+// tile; the leader CTA issues one MMA for both and the tensor cores read the other half of B from the peer's shared memory.
+// Per k-step and SM that is 32 KiB written by TMA and 32 KiB read by the MMA -- the single-CTA version (128 x 256 tiles, B
+// multicast) moved 48 + 48 KiB, above what the 128 B/clk shared memory sustains next to a full-rate tensor pipe, and topped
+// out near 1000 TFLOP/s.
 //
 //   warp 0      : TMA producer (one elected lane)
 //   warp 1      : TMEM allocator + MMA issuer (one elected lane)
@@ -45,7 +48,7 @@ struct EpiTraits {
 template <int BN, int EPI>
 struct GemmCfg {
   static constexpr int A_BYTES = kBM * kBK * 2;
-  static constexpr int B_BYTES = BN * kBK * 2;
+  static constexpr int B_BYTES = (BN / 2) * kBK * 2;      // this CTA's half of the pair's B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int EPI_BYTES = 8 * EpiTraits<EPI>::BOXES_PER_WARP_SMEM * kBoxBytes;   // 32 or 64 KiB
   static constexpr int FIT = (227 * 1024 - 2048 - EPI_BYTES) / STAGE_BYTES;
@@ -106,22 +109,22 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 1) {
     if (elect_one()) {
       for (int s = 0; s < Cfg::STAGES; ++s) {
-        mbar_init(&full_bar[s], 1);
-        mbar_init(&empty_bar[s], 2);   // released by the MMA warps of BOTH CTAs (the peer multicasts into our stage)
+        mbar_init(&full_bar[s], 1);    // used in the leader only: its producer's arrive + the bytes of BOTH CTAs' loads
+        mbar_init(&empty_bar[s], 1);   // released in both CTAs by the leader's MMA commit
       }
       for (int s = 0; s < 2; ++s) {
-        mbar_init(&tfull_bar[s], 1);
-        mbar_init(&tempty_bar[s], 8);
+        mbar_init(&tfull_bar[s], 1);   // the leader's commit, multicast
+        mbar_init(&tempty_bar[s], 16); // used in the leader only: the epilogue warps of both CTAs
       }
       for (int s = 0; s < 8; ++s) mbar_init(&aux_bar[s], 1);
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+    tmem_alloc_2sm<Cfg::TMEM_COLS>(tmem_slot);
   }
   tc_fence_before();
   __syncthreads();
-  cluster_sync_all();      // the peer's barriers are initialised before anything is multicast into it
+  cluster_sync_all();      // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -140,23 +143,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          const uint32_t lbar = mapa_u32(smem_u32(&full_bar[stage]), 0);   // the leader's barrier counts the pair's bytes
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
           if constexpr (!A_MN) {
-            tma_load_2d(sa, &tmA, &full_bar[stage], kb * kBK, m_blk * kBM);
+            tma_load_2d_2sm(sa, &tmA, lbar, kb * kBK, m_blk * kBM);
           } else {
 #pragma unroll
-            for (int i = 0; i < kBM / 64; ++i)
-              tma_load_2d(sa + i * (kBK * 128), &tmA, &full_bar[stage], m_blk * kBM + i * 64, kb * kBK);
+            for (int i = 0; i < kBM / 64; ++i) tma_load_2d_2sm(sa + i * (kBK * 128), &tmA, lbar, m_blk * kBM + i * 64, kb * kBK);
           }
-          // our half of the shared B tile, multicast into both CTAs of the pair
+          // our half (BN/2 rows of N) of the pair's B tile
           if constexpr (!B_MN) {
-            tma_load_2d_mcast(sb + rank * (BN / 2) * 128, &tmB, &full_bar[stage], kb * kBK, n_blk * BN + rank * (BN / 2), 3);
+            tma_load_2d_2sm(sb, &tmB, lbar, kb * kBK, n_blk * BN + rank * (BN / 2));
           } else {
 #pragma unroll
-            for (int i = 0; i < BN / 128; ++i) {
-              const int bx = rank * (BN / 128) + i;
-              tma_load_2d_mcast(sb + bx * (kBK * 128), &tmB, &full_bar[stage], n_blk * BN + bx * 64, kb * kBK, 3);
-            }
+            for (int i = 0; i < BN / 128; ++i)
+              tma_load_2d_2sm(sb + i * (kBK * 128), &tmB, lbar, n_blk * BN + (rank * (BN / 128) + i) * 64, kb * kBK);
           }
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -164,9 +165,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (elect_one()) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN, A_MN, B_MN);
+    // ------------------------------------------------------------------ MMA issuer (leader CTA of the pair only)
+    if (rank == 0 && elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * kBM, BN, A_MN, B_MN);
       // K-major: 8-row groups 1024 B apart (SBO); one 128 B swizzle atom along K (LBO unused).
       // MN-major: 64-element MN atoms kBK*128 B apart (LBO); 8-k groups 1024 B apart (SBO).
       constexpr uint32_t lbo_a = A_MN ? kBK * 128 : 0, lbo_b = B_MN ? kBK * 128 : 0;
@@ -192,11 +193,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint64_t db = umma_desc_sw128(sa + Cfg::A_BYTES, lbo_b, 1024);
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k)
-            umma_ss(tmem_d, da + (uint64_t)(k * kstep_a), db + (uint64_t)(k * kstep_b), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-          umma_commit_mcast(&empty_bar[stage], 3);  // slot reusable (in both CTAs) once these MMAs retire
+            umma_ss_2sm(tmem_d, da + (uint64_t)(k * kstep_a), db + (uint64_t)(k * kstep_b), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          umma_commit_2sm(&empty_bar[stage], 3);    // slot reusable (in both CTAs) once these MMAs retire
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[as]);  // accumulator complete
+        umma_commit_2sm(&tfull_bar[as], 3);         // accumulator complete (both CTAs' epilogues)
       }
     }
     __syncwarp();
@@ -326,17 +327,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[as]), 0));   // the leader's MMA warp waits for both CTAs
     }
     if (lane == 0) bulk_wait0();   // all of this warp's stores / reductions are complete before the CTA may exit
     __syncwarp();
   }
   tc_fence_before();
   __syncthreads();
-  cluster_sync_all();      // nobody leaves while the peer may still multicast into / signal this CTA
+  cluster_sync_all();      // nobody leaves while the peer may still read our B half / signal this CTA
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    tmem_dealloc_2sm<Cfg::TMEM_COLS>(tmem_base);
   }
 }
 
