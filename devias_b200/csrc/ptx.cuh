@@ -221,8 +221,10 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t rank) 
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
   return r;
 }
+// (relaxed: what the waiter consumes was produced through tensor memory and is ordered by tcgen05.wait / tcgen05.fence;
+//  a .release at cluster scope costs a MEMBAR.ALL + ERRBAR per arrive -- 29 % of the epilogue warps' stall samples)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // tile load into OUR shared memory whose bytes are counted on a barrier of the pair's leader CTA
 __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* tm, uint32_t leader_bar, int x, int y) {
