@@ -350,7 +350,8 @@ def main():
                        'clips_per_gpu': B, 'global_batch': B * world, 'parallelism': f'dp{world}',
                        'l2': 'per-step working set (activations + weights, several GB) far exceeds the 126 MB L2; no flush needed',
                        'loss': loss_val, 'launch_mode': ('eager' if graphed is None else 'cuda-graph replay of the whole step' if world == 1 else
-                                       'cuda graph (fwd+bwd) -> NCCL all-reduce of flat fp32 gradient buckets -> cuda graph (AdamW)')},
+                                       'three cuda graphs per step (fwd+bwd down to block 3 | bwd of blocks 0-2 | AdamW); the NCCL all-reduce of the upper '
+                                       'gradients (flat fp32 arena) runs between them, overlapping the lower backward')},
             'clocks': clk,
             'gpu_launches': int(launches),
             'roofline': {'kernel': 'gemm_bf16_kernel (tcgen05/TMEM/TMA)', 'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf,

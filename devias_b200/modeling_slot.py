@@ -393,10 +393,13 @@ class VisionTransformer(nn.Module):
             bs, num_slots, _ = slots.size()
             slots = slots.reshape(-1, 768)
             slots_head = self._head_linear(self.fc_dropout(slots))
-            probs = F.softmax(slots_head, dim=-1).view(bs, num_slots, -1)
             C = self.num_classes
-            a_idx = torch.argmax(probs[:, :, :C].max(dim=-1).values, dim=1)
-            s_idx = torch.argmax(probs[:, :, C:C + self.num_scene_classes].max(dim=-1).values, dim=1)
+            if slots_head.dtype == torch.float32 and num_slots <= 8 and slots_head.shape[-1] >= C + self.num_scene_classes:
+                a_idx, s_idx = ops.slot_select(slots_head.detach(), num_slots, C, self.num_scene_classes)
+            else:
+                probs = F.softmax(slots_head, dim=-1).view(bs, num_slots, -1)
+                a_idx = torch.argmax(probs[:, :, :C].max(dim=-1).values, dim=1)
+                s_idx = torch.argmax(probs[:, :, C:C + self.num_scene_classes].max(dim=-1).values, dim=1)
             ar = torch.arange(bs, device=slots.device)
             s3, h3 = slots.view(bs, num_slots, -1), slots_head.view(bs, num_slots, -1)
             mask_predictions = self.mask_predictor(slots)

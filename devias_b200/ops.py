@@ -195,6 +195,19 @@ def skinny_outer(a: torch.Tensor, b: torch.Tensor, want_colsum=False):
     return c, cs
 
 
+def slot_select(slots_head: torch.Tensor, num_slots: int, n_action: int, n_scene: int):
+    """slots_head fp32 [B*S, >= n_action + n_scene] -> (action slot index [B], scene slot index [B]) int64"""
+    _need_cuda(slots_head)
+    assert slots_head.dtype == torch.float32 and slots_head.dim() == 2 and slots_head.stride(1) == 1
+    B = slots_head.shape[0] // num_slots
+    a = torch.empty(B, device=slots_head.device, dtype=torch.int64)
+    s = torch.empty(B, device=slots_head.device, dtype=torch.int64)
+    rc = _lib.lib().devias_slot_select(slots_head.data_ptr(), slots_head.stride(0), B, num_slots, n_action, n_scene, a.data_ptr(),
+                                       s.data_ptr(), _stream())
+    _lib.check(rc, 'slot_select')
+    return a, s
+
+
 def flash_attn_fwd(qkv: torch.Tensor, B: int, N: int, H: int, need_lse=True):
     """qkv bf16 [B*N, 3*H*64] -> (out bf16 [B*N, H*64], lse2 fp32 [B, H, Npad] | None)"""
     _need_cuda(qkv)

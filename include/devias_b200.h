@@ -129,6 +129,12 @@ int devias_scale_rows_cast(const float* in, void* out, int rows, int cols, const
                            void* stream);
 int devias_patchify(const void* clip, int clip_dtype, void* out, int batch, int chans, int frames, int height, int width,
                     void* stream);
+/* ---- head: slot selection (model/modeling_slot.py:396-404; model/modeling_slot_fusion.py:376-386) -------------
+ * logits [batch*slots, ld] fp32 (n_action + n_scene used columns) -> per clip the slot whose softmax row has the largest
+ * action-class probability / scene-class probability (int64 [batch] each; first maximum wins, as torch.argmax). */
+int devias_slot_select(const float* logits, int64_t ld, int batch, int slots, int n_action, int n_scene, long long* action_idx,
+                       long long* scene_idx, void* stream);
+
 /* diagnostic: the bare TMA token stream of the slot kernels (same tensor map / ring / tile split, no arithmetic) */
 int devias_debug_token_stream(const float* tokens, int batch, int n_tokens, int stages, float* scratch, void* stream);
 

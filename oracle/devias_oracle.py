@@ -317,6 +317,65 @@ def student_forward(sd: State, clips: Tensor, num_classes: int, num_scene_classe
     return head_matching(sd, slots, attn, num_classes, num_scene_classes)
 
 
+
+# ----------------------------------------------------------------------------------------------
+# downstream fusion model (model/modeling_slot_fusion.py) -- SURVEY.md section 8f row N4
+# ----------------------------------------------------------------------------------------------
+
+def synth_fusion_state_dict(num_classes=101, num_scene_classes=365, num_latents=2, agg_depth=4, depth=2,
+                            downstream_nb_classes=50, use_input_ln=True, seed=0) -> State:
+    """state_dict of slot_fusion_vit_base_patch16_224(head_type='mlp', slot_fusion_method='concat'): the pre-training
+    student's encoder / aggregation / head tensors plus action_norm, scene_norm and the MLPHead fusion_head
+    (model/modeling_slot_fusion.py:23-38, 285-306).  No mask_predictor in this model."""
+    sd = synth_state_dict(num_classes=num_classes, num_scene_classes=num_scene_classes, num_latents=num_latents,
+                          agg_depth=agg_depth, agg_weights_tie=True, depth=depth, seed=seed)
+    sd = {k: v for k, v in sd.items() if not k.startswith('mask_predictor.')}
+    rs = np.random.RandomState(seed + 1000)
+    D = 768
+
+    def lin(prefix, out_f, in_f, std=0.03):
+        sd[prefix + '.weight'] = _trunc_normal(rs, (out_f, in_f), std)
+        sd[prefix + '.bias'] = _trunc_normal(rs, (out_f,), 0.02)
+
+    def ln(prefix, dim):
+        sd[prefix + '.weight'] = 1.0 + _trunc_normal(rs, (dim,), 0.1)
+        sd[prefix + '.bias'] = _trunc_normal(rs, (dim,), 0.02)
+
+    ln('action_norm', D); ln('scene_norm', D)
+    lin('fusion_head.fc_action_down', D // 2, D); lin('fusion_head.fc_scene_down', D // 2, D)
+    ln('fusion_head.fc_action_ln', D // 2); ln('fusion_head.fc_scene_ln', D // 2)
+    if use_input_ln:
+        ln('fusion_head.fc_input_ln', D)
+    lin('fusion_head.classifier', downstream_nb_classes, D)
+    return sd
+
+
+def fusion_forward(sd: State, clips: Tensor, num_classes: int, num_scene_classes=365, depth: Optional[int] = None,
+                   agg_depth: Optional[int] = None, use_input_ln=True, eps=1e-6):
+    """model/modeling_slot_fusion.py:364-403 ('concat' + MLPHead :40-54; note the head's fc_action_* modules serve BOTH tokens)."""
+    tokens = forward_features(sd, clips, depth)
+    slots, _ = aggregation_block(sd, tokens, depth=agg_depth)
+    bs, S, D = slots.shape
+    flat = slots.reshape(-1, D)
+    slots_head = F.linear(flat, sd['head.weight'], sd['head.bias'])
+    probs = F.softmax(slots_head, dim=-1).view(bs, S, -1)
+    a_idx = torch.argmax(probs[:, :, :num_classes].max(dim=-1).values, dim=1)
+    s_idx = torch.argmax(probs[:, :, num_classes:num_classes + num_scene_classes].max(dim=-1).values, dim=1)
+    ar = torch.arange(bs)
+    a = F.layer_norm(flat.view(bs, S, -1)[ar, a_idx], (D,), sd['action_norm.weight'], sd['action_norm.bias'], eps)
+    c = F.layer_norm(flat.view(bs, S, -1)[ar, s_idx], (D,), sd['scene_norm.weight'], sd['scene_norm.bias'], eps)
+    inp = torch.cat((a, c), dim=1)
+
+    def down(t):
+        t = F.linear(t, sd['fusion_head.fc_action_down.weight'], sd['fusion_head.fc_action_down.bias'])
+        return F.layer_norm(t, (D // 2,), sd['fusion_head.fc_action_ln.weight'], sd['fusion_head.fc_action_ln.bias'], 1e-5)
+
+    out = torch.cat([down(a), down(c)], dim=1)
+    if use_input_ln:
+        out = F.layer_norm(out, (D,), sd['fusion_head.fc_input_ln.weight'], sd['fusion_head.fc_input_ln.bias'], 1e-5)
+    out = F.linear(F.relu(out), sd['fusion_head.classifier.weight'], sd['fusion_head.classifier.bias'])
+    return inp, out, (a_idx, s_idx)
+
 # ----------------------------------------------------------------------------------------------
 # training objective (utils/loss/train_loss.py:85-187) -- S=2.. small; Hungarian by brute force
 # ----------------------------------------------------------------------------------------------

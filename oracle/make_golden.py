@@ -141,6 +141,22 @@ def main():
     np.savez_compressed(os.path.join(OUT, 'teacher_d12.npz'), token=_np(tok), logits=_np(logit))
     print('teacher', float(logit.abs().max()))
 
+    # downstream fusion model (model/modeling_slot_fusion.py), head_type='mlp', concat
+    msf = importlib.import_module('model.modeling_slot_fusion')
+    fsd = O.synth_fusion_state_dict(num_classes=101, depth=2, agg_depth=4, downstream_nb_classes=50, seed=8)
+    from functools import partial
+    with contextlib.redirect_stdout(io.StringIO()):
+        fm = msf.VisionTransformer(patch_size=16, embed_dim=768, depth=2, num_heads=12, mlp_ratio=4, qkv_bias=True,
+                                   norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), num_classes=101, num_latents=2,
+                                   head_type='mlp', agg_weights_tie=True, agg_depth=4, slot_fusion_method='concat',
+                                   downstream_nb_classes=50, use_input_ln=True)
+    assert set(fm.state_dict().keys()) == set(fsd.keys()), set(fm.state_dict().keys()) ^ set(fsd.keys())
+    fm.load_state_dict(fsd); fm.eval()
+    with torch.no_grad():
+        finp, fout = fm(O.synth_clips(2, seed=4))
+    np.savez_compressed(os.path.join(OUT, 'fusion_d2.npz'), features=_np(finp), logits=_np(fout))
+    print('fusion', float(fout.abs().max()))
+
     # sinusoid table known answers
     tab = ns.modeling_slot.get_sinusoid_encoding_table(1568, 768)
     np.savez_compressed(os.path.join(OUT, 'sinusoid.npz'), rows=_np(tab[0, [0, 1, 2, 777, 1567]]), sum=np.float64(tab.double().sum().item()))

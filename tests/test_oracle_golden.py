@@ -119,3 +119,31 @@ def test_teacher_forward_golden():
     assert_close(tok, g['token'], TOL, 'teacher token')
     assert_close(logit, g['logits'], TOL, 'teacher logits')
     assert int(logit.argmax()) == int(g['logits'].argmax())
+
+
+def test_fusion_forward_golden():
+    """downstream fusion model (model/modeling_slot_fusion.py): oracle restatement vs the reference's own output"""
+    g = golden('fusion_d2')
+    sd = O.synth_fusion_state_dict(num_classes=101, depth=2, agg_depth=4, downstream_nb_classes=50, seed=8)
+    with torch.no_grad():
+        inp, out, _ = O.fusion_forward(sd, O.synth_clips(2, seed=4), 101, depth=2)
+    assert_close(inp, g['features'], TOL, 'fusion features')
+    assert_close(out, g['logits'], TOL, 'fusion logits')
+    assert (out.argmax(-1).numpy() == g['logits'].argmax(-1)).all()
+
+
+def test_fusion_state_dict_keys_match_reference_layout():
+    """the drop-in's module tree carries exactly the reference's parameter names and shapes (constructed on CPU)"""
+    import contextlib, io
+    from functools import partial
+    from devias_b200.modeling_slot_fusion import VisionTransformer
+    sd = O.synth_fusion_state_dict(num_classes=101, depth=2, agg_depth=4, downstream_nb_classes=50, seed=8)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = VisionTransformer(patch_size=16, embed_dim=768, depth=2, num_heads=12, mlp_ratio=4, qkv_bias=True,
+                              norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), num_classes=101, num_latents=2, head_type='mlp',
+                              agg_weights_tie=True, agg_depth=4, slot_fusion_method='concat', downstream_nb_classes=50)
+    own = m.state_dict()
+    assert set(own.keys()) == set(sd.keys())
+    for k, v in sd.items():
+        assert tuple(own[k].shape) == tuple(v.shape), k
+    m.load_state_dict(sd)
