@@ -9,6 +9,7 @@
 //                                 128B-swizzled smem as the A operand of the second MMA, running O in registers)
 // Backward kernels live below (dQ / dK / dV with recomputed probabilities).
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -250,6 +251,233 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   }
 }
 
+
+// =====================================================================================================================
+// Forward, second generation: FOUR small CTAs per SM instead of two big ones.
+// ncu on the first kernel: MUFU (ex2) 48 % and tensor pipe 21 % busy, one softmax warp per scheduler and CTA stalled on its
+// own serial chain (TMEM load -> max -> 64 ex2 -> pack -> TMEM store -> barrier), i.e. latency bound with two CTAs per SM.
+// Here a CTA is 5 warps with <= 96 registers and 128 TMEM columns (S/P 64 + O 64), so four fit on an SM and their chains
+// interleave on the shared MUFU / tensor pipes:
+//   warp 0     : control -- one lane issues the TMA loads (Q once, K_j / V_j through a 2-stage ring) AND the MMAs
+//                (S_j = Q K_j^T;  after the softmax of tile j:  O += P_j V_j, then at once S_{j+1});  tcgen05 ops of one thread
+//                retire in order, so S_{j+1} cannot overwrite P_j early and `s_full` of tile j implies P_{j-1} V_{j-1} landed
+//   warps 1..4 : softmax, thread = query row, in 16-column chunks to stay small: pass 1 row maximum, lazy rescale of O
+//                (only when the maximum moved by more than 8 in the exp2 domain), pass 2 re-reads the chunk, ex2, packs P_j
+//                as bf16 pairs over the S columns already consumed (the MMA reads P from tensor memory)
+constexpr int kFa2Threads = 160;
+struct Fa2Smem {
+  static constexpr int OFF_Q = 0;                                  // 16 KiB
+  static constexpr int OFF_K = OFF_Q + kQT * kHD * 2;              // 2 x 8 KiB
+  static constexpr int OFF_V = OFF_K + 2 * kKT * kHD * 2;          // 2 x 8 KiB
+  static constexpr int OFF_BAR = OFF_V + 2 * kKT * kHD * 2;
+  static constexpr int BYTES = OFF_BAR + 128 + 1024;
+};
+
+__global__ void __launch_bounds__(kFa2Threads, 4)
+flash_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const FaParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Fa2Smem::OFF_BAR);
+  uint64_t* q_full = bars;                 // 1
+  uint64_t* kv_full = bars + 1;            // 2
+  uint64_t* kv_empty = bars + 3;           // 2
+  uint64_t* s_full = bars + 5;             // 1
+  uint64_t* p_full = bars + 6;             // 1 (4 warp arrivals)
+  uint64_t* o_done = bars + 7;             // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5;
+  const int q_tiles = (p.N + kQT - 1) / kQT;
+  const int qt = blockIdx.x % q_tiles;
+  const int bh = blockIdx.x / q_tiles;
+  const int h = bh % p.H, b = bh / p.H;
+  const int q0 = qt * kQT;
+  const int T = (p.N + kKT - 1) / kKT;     // key tiles
+  const int D = p.H * kHD;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      prefetch_tmap(&tmQ);
+      prefetch_tmap(&tmKV);
+      mbar_init(q_full, 1);
+      for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+      mbar_init(s_full, 1);
+      mbar_init(p_full, 4);
+      mbar_init(o_done, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<128>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tm_s = tmem, tm_o = tmem + 64;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(kQT, kKT, false, false);   // S = Q K^T : both K-major
+      constexpr uint32_t idesc_o = umma_idesc_bf16(kQT, kHD, false, true);    // O = P V   : A from TMEM, B (=V) MN-major
+      constexpr uint32_t kTile = kKT * kHD * 2;
+      auto load_kv = [&](int j) {
+        const int st = j & 1;
+        mbar_arrive_expect_tx(&kv_full[st], 2 * kTile);
+        tma_load_3d(smem + Fa2Smem::OFF_K + st * kTile, &tmKV, &kv_full[st], D + h * kHD, j * kKT, b);
+        tma_load_3d(smem + Fa2Smem::OFF_V + st * kTile, &tmKV, &kv_full[st], 2 * D + h * kHD, j * kKT, b);
+      };
+      auto issue_s = [&](int j) {
+        const int st = j & 1;
+        mbar_wait(&kv_full[st], (j >> 1) & 1);
+        tc_fence_after();
+        const uint64_t da = umma_desc_sw128(smem_u32(smem + Fa2Smem::OFF_Q), 0, 1024);
+        const uint64_t db = umma_desc_sw128(smem_u32(smem + Fa2Smem::OFF_K + st * kTile), 0, 1024);
+#pragma unroll
+        for (int k = 0; k < kHD / 16; ++k) umma_ss(tm_s, da + 2 * k, db + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(s_full);
+      };
+      mbar_arrive_expect_tx(q_full, kQT * kHD * 2);
+      tma_load_3d(smem + Fa2Smem::OFF_Q, &tmQ, q_full, h * kHD, q0, b);
+      load_kv(0);
+      if (T > 1) load_kv(1);
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      for (int j = 0; j < T; ++j) {
+        const int st = j & 1;
+        mbar_wait(p_full, j & 1);            // P_j is in TMEM and any rescaling of O has been fenced
+        tc_fence_after();
+        const uint64_t db = umma_desc_sw128(smem_u32(smem + Fa2Smem::OFF_V + st * kTile), kKT * 128, 1024);
+#pragma unroll
+        for (int k = 0; k < kKT / 16; ++k) umma_ts(tm_o, tm_s + 8 * k, db + 128 * k, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+        umma_commit(&kv_empty[st]);
+        if (j + 1 < T) {
+          issue_s(j + 1);                    // queued behind P_j V_j on the tensor pipe
+          if (j + 2 < T) {
+            mbar_wait(&kv_empty[st], (j >> 1) & 1);   // P_j V_j retired: its K/V stage is free for tile j + 2
+            load_kv(j + 2);
+          }
+        } else {
+          umma_commit(o_done);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;                          // TMEM lane quarter this warp may access (warps 1..4 -> 1, 2, 3, 0)
+    const int lane = (int)lane_id();
+    const int r = q * 32 + lane;                     // query row inside the tile == TMEM lane
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    float m = -INFINITY, l = 0.f;
+    const uint64_t cc = f2_pack(p.scale_log2, p.scale_log2);
+    for (int j = 0; j < T; ++j) {
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      const int valid = p.N - j * kKT;               // keys valid in this tile (>= 64 except the last)
+      uint64_t sum2 = 0ull;
+      auto tile = [&](auto ragged_tag) {             // the ragged last tile masks its tail; all others take the bare path
+        constexpr bool RAGGED = decltype(ragged_tag)::value;
+        // ---- pass 1: row maximum.  Chunk loads are software-pipelined: tcgen05.wait::ld covers every load issued so far, so
+        // the next chunk is requested right after the wait and its latency hides behind the arithmetic on the current one.
+        uint32_t sa[16], sb[16];
+        float mx = -INFINITY;
+        tmem_ld_32x32b_x16(tm_s + lane_sel, sa);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t (&cur)[16] = (c & 1) ? sb : sa;
+          uint32_t (&nxt)[16] = (c & 1) ? sa : sb;
+          tmem_ld_wait();
+          tmem_ld_32x32b_x16(tm_s + lane_sel + 16 * ((c + 1) & 3), nxt);      // c = 3: chunk 0 again, for pass 2
+          float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float v = (!RAGGED || 16 * c + i < valid) ? __uint_as_float(cur[i]) : -INFINITY;
+            m4[i & 3] = fmaxf(m4[i & 3], v);
+          }
+          mx = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
+        }
+        const float m_run = fmaxf(m, mx * p.scale_log2);   // scale > 0: max(c s) = c max(s)
+        if (__any_sync(0xffffffffu, m_run > m + 8.0f)) {
+          const float alpha = fast_exp2(m - m_run);       // 0 on the first tile (m = -inf)
+          if (j > 0) {                                    // (s_full of tile j implies P_{j-1} V_{j-1} has been accumulated)
+            tmem_ld_wait();                               // chunk 0 of pass 2 (in sa) has landed; its registers stay live
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              uint32_t t[16];
+              tmem_ld_32x32b_x16(tm_o + lane_sel + 16 * c, t);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * alpha);
+              tmem_st_32x32b_x16(tm_o + lane_sel + 16 * c, t);
+            }
+          }
+          l *= alpha;
+          m = m_run;
+        }
+        // ---- pass 2: P_j = exp2(c s - m) as bf16 pairs, written over the S columns this thread has already consumed
+        const uint64_t negm = f2_pack(-m, -m);
+        sum2 = 0ull;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t (&cur)[16] = (c & 1) ? sb : sa;
+          uint32_t (&nxt)[16] = (c & 1) ? sa : sb;
+          tmem_ld_wait();
+          if (c < 3) tmem_ld_32x32b_x16(tm_s + lane_sel + 16 * (c + 1), nxt);
+          uint32_t pk[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float x0 = (!RAGGED || 16 * c + 2 * i < valid) ? __uint_as_float(cur[2 * i]) : -INFINITY;
+            const float x1 = (!RAGGED || 16 * c + 2 * i + 1 < valid) ? __uint_as_float(cur[2 * i + 1]) : -INFINITY;
+            const uint64_t y = f2_fma(f2_pack(x0, x1), cc, negm);
+            const float e0 = fast_exp2(f2_lo(y)), e1 = fast_exp2(f2_hi(y));
+            sum2 = f2_add(sum2, f2_pack(e0, e1));
+            pk[i] = pack_bf16(e0, e1);
+          }
+          tmem_st_32x32b_x8(tm_s + lane_sel + 8 * c, pk);
+        }
+      };
+      if (valid < kKT) tile(std::true_type{}); else tile(std::false_type{});
+      l += f2_lo(sum2) + f2_hi(sum2);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+    }
+    mbar_wait(o_done, 0);
+    tc_fence_after();
+    const float inv = 1.0f / l;
+    const int qi = q0 + r;
+    __nv_bfloat16* dst = p.out + ((long long)b * p.N + qi) * p.ldo + h * kHD;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      uint32_t t[16];
+      tmem_ld_32x32b_x16(tm_o + lane_sel + 16 * c, t);
+      tmem_ld_wait();
+      if (qi < p.N) {
+        uint4 v0, v1;
+        v0.x = pack_bf16(__uint_as_float(t[0]) * inv, __uint_as_float(t[1]) * inv);
+        v0.y = pack_bf16(__uint_as_float(t[2]) * inv, __uint_as_float(t[3]) * inv);
+        v0.z = pack_bf16(__uint_as_float(t[4]) * inv, __uint_as_float(t[5]) * inv);
+        v0.w = pack_bf16(__uint_as_float(t[6]) * inv, __uint_as_float(t[7]) * inv);
+        v1.x = pack_bf16(__uint_as_float(t[8]) * inv, __uint_as_float(t[9]) * inv);
+        v1.y = pack_bf16(__uint_as_float(t[10]) * inv, __uint_as_float(t[11]) * inv);
+        v1.z = pack_bf16(__uint_as_float(t[12]) * inv, __uint_as_float(t[13]) * inv);
+        v1.w = pack_bf16(__uint_as_float(t[14]) * inv, __uint_as_float(t[15]) * inv);
+        reinterpret_cast<uint4*>(dst)[2 * c] = v0;
+        reinterpret_cast<uint4*>(dst)[2 * c + 1] = v1;
+      }
+    }
+    if (p.lse2 != nullptr) {
+      if (qi < p.N) p.lse2[((long long)b * p.H + h) * p.Npad + qi] = m + log2f(l);
+      else if (qi < p.Npad) p.lse2[((long long)b * p.H + h) * p.Npad + qi] = INFINITY;   // padded queries: P = 0 in the backward
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<128>(tmem);
+  }
+}
 
 // =====================================================================================================================
 // Backward.  One CTA per (clip, head, 128-key tile); loop over 128-query tiles.  dK/dV accumulate in TMEM for the whole
@@ -588,8 +816,12 @@ extern "C" int devias_flash_attn_fwd(const void* qkv, void* out, float* lse2, in
   rc = make_qkv_tmap(&tmKV, qkv, batch, seq, 3 * D, kKT);
   if (rc) return rc;
   static bool attr_done = false;
+  static int generation = 2;               // DEVIAS_FLASH_FWD=1 selects the first-generation kernel (two CTAs per SM)
   if (!attr_done) {
     DV_CHECK_CUDA(cudaFuncSetAttribute(flash_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FaSmem::BYTES));
+    DV_CHECK_CUDA(cudaFuncSetAttribute(flash_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Fa2Smem::BYTES));
+    const char* e = getenv("DEVIAS_FLASH_FWD");
+    if (e != nullptr && e[0] == '1') generation = 1;
     attr_done = true;
   }
   FaParams p{batch, seq, heads, (seq + 127) / 128 * 128, scale * 1.4426950408889634f, static_cast<__nv_bfloat16*>(out),
@@ -597,7 +829,8 @@ extern "C" int devias_flash_attn_fwd(const void* qkv, void* out, float* lse2, in
   const int q_tiles = (seq + kQT - 1) / kQT;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int prof = prof_begin(DEVIAS_PROF_ATTN, 4.0 * batch * heads * (double)seq * seq * kHD, s);
-  flash_fwd_kernel<<<batch * heads * q_tiles, kFaThreads, FaSmem::BYTES, s>>>(tmQ, tmKV, p);
+  if (generation == 2) flash_fwd2_kernel<<<batch * heads * q_tiles, kFa2Threads, Fa2Smem::BYTES, s>>>(tmQ, tmKV, p);
+  else flash_fwd_kernel<<<batch * heads * q_tiles, kFaThreads, FaSmem::BYTES, s>>>(tmQ, tmKV, p);
   prof_end(prof, s);
   DV_CHECK_CUDA(cudaGetLastError());
   count_launch();
