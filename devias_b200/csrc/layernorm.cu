@@ -73,7 +73,8 @@ __global__ void __launch_bounds__(256, 3) layernorm_bwd_kernel(const void* __res
                                                                const float* __restrict__ gamma, const float* d_resid,
                                                                float* dx, __nv_bfloat16* __restrict__ dx_bf16,
                                                                float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                               float* __restrict__ dx_colsum, int M) {
+                                                               float* __restrict__ dx_colsum,
+                                                               const float* __restrict__ bscale, int rows_per_scale, int M) {
   constexpr int V = RowRegs<D>::V;
   extern __shared__ float4 ln_acc[];                 // [3][8 warps][D/4]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
@@ -85,6 +86,8 @@ __global__ void __launch_bounds__(256, 3) layernorm_bwd_kernel(const void* __res
   const float4* g4 = reinterpret_cast<const float4*>(gamma);
   for (int row = blockIdx.x * nwarp + warp; row < M; row += gridDim.x * nwarp) {
     const float mu = __ldg(mean + row), r = __ldg(rstd + row);
+    // per-sample factor of the branch that consumes this gradient next (drop-path): applied to the bf16 copy and its column sums
+    const float sc = bscale != nullptr ? __ldg(bscale + row / rows_per_scale) : 1.0f;
     const float4* xr = reinterpret_cast<const float4*>(x + (long long)row * D);
     float4 xh[V], d[V];
     float s1 = 0.f, s2 = 0.f;
@@ -130,6 +133,7 @@ __global__ void __launch_bounds__(256, 3) layernorm_bwd_kernel(const void* __res
         o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
       }
       if (dx != nullptr) reinterpret_cast<float4*>(dx + (long long)row * D)[lane + 32 * i] = o;
+      o.x *= sc; o.y *= sc; o.z *= sc; o.w *= sc;
       if (dx_bf16 != nullptr)
         reinterpret_cast<uint2*>(dx_bf16 + (long long)row * D)[lane + 32 * i] = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
       if (dx_colsum != nullptr) {
@@ -204,9 +208,12 @@ extern "C" int devias_layernorm_fwd(const float* x, const float* gamma, const fl
 
 extern "C" int devias_layernorm_bwd(const void* dy, int dy_is_bf16, const float* x, const float* mean, const float* rstd,
                                     const float* gamma, const float* d_resid, float* dx, void* dx_bf16, float* dgamma,
-                                    float* dbeta, float* dx_colsum, int rows, int dim, void* stream) {
+                                    float* dbeta, float* dx_colsum, const float* bf16_row_scale, int rows_per_scale, int rows, int dim,
+                                    void* stream) {
   using namespace dv;
   DV_REQUIRE(dy && x && mean && rstd && gamma, "null pointer");
+  DV_REQUIRE(bf16_row_scale == nullptr || rows_per_scale > 0, "rows_per_scale");
+  if (bf16_row_scale == nullptr) rows_per_scale = 1;
   DV_REQUIRE(dim == 768, "only dim = 768 is instantiated");
   if (rows <= 0) return DEVIAS_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -222,10 +229,12 @@ extern "C" int devias_layernorm_bwd(const void* dy, int dy_is_bf16, const float*
   }
   if (dy_is_bf16)
     layernorm_bwd_kernel<768, true><<<grid, 256, kLnSmem, s>>>(dy, x, mean, rstd, gamma, d_resid, dx,
-                                                         static_cast<__nv_bfloat16*>(dx_bf16), dgamma, dbeta, dx_colsum, rows);
+                                                         static_cast<__nv_bfloat16*>(dx_bf16), dgamma, dbeta, dx_colsum, bf16_row_scale,
+                                                         rows_per_scale, rows);
   else
     layernorm_bwd_kernel<768, false><<<grid, 256, kLnSmem, s>>>(dy, x, mean, rstd, gamma, d_resid, dx,
-                                                          static_cast<__nv_bfloat16*>(dx_bf16), dgamma, dbeta, dx_colsum, rows);
+                                                          static_cast<__nv_bfloat16*>(dx_bf16), dgamma, dbeta, dx_colsum, bf16_row_scale,
+                                                         rows_per_scale, rows);
   DV_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return DEVIAS_OK;

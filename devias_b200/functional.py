@@ -16,12 +16,14 @@ from . import ops
 # side channel: the LayerNorm-backward kernel that produces a residual-stream gradient (fp32) also
 # emits its bf16 copy (the operand of the next dgrad/wgrad GEMMs).  autograd only carries the fp32
 # tensor between Functions; the copy travels here, keyed by (data_ptr, version).
+# The copy may already carry the per-sample drop-path factor of the branch that consumes it next (`scale`, matched by
+# identity) and comes with its column sums (= the bias gradient of that branch's last linear layer).
 _bf16_of = {}
 
 
-def _stash_bf16(dx: torch.Tensor, dxb: torch.Tensor):
+def _stash_bf16(dx: torch.Tensor, dxb: torch.Tensor, scale=None, colsum=None):
     _bf16_of.clear()
-    _bf16_of[(dx.data_ptr(), dx._version)] = dxb
+    _bf16_of[(dx.data_ptr(), dx._version)] = (dxb, scale, colsum)
 
 
 def _is_ours(dx: torch.Tensor) -> bool:
@@ -30,10 +32,22 @@ def _is_ours(dx: torch.Tensor) -> bool:
 
 
 def _take_bf16(dx: torch.Tensor) -> torch.Tensor:
+    """unscaled bf16 copy of a residual-stream gradient"""
     t = _bf16_of.pop((dx.data_ptr(), dx._version), None)
-    if t is not None and t.shape == dx.shape:
-        return t
+    if t is not None and t[1] is None and t[0].shape == dx.shape:
+        return t[0]
     return ops.cast_bf16(dx.contiguous())
+
+
+def _take_scaled(dx: torch.Tensor, scale, rows_per_scale: int):
+    """(bf16(dx * scale per sample), column sums of it | None): straight from the producing LayerNorm backward when it was told
+    this consumer's scale, otherwise by the stand-alone cast kernel."""
+    t = _bf16_of.pop((dx.data_ptr(), dx._version), None)
+    if t is not None and t[1] is scale and t[0].shape == dx.shape:
+        return t[0], t[2]
+    if scale is None:
+        return ops.cast_bf16(dx.contiguous()), None
+    return ops.scale_rows_cast(dx, scale, rows_per_scale), None
 
 
 def _flat_zeros(like_list, device):
@@ -87,19 +101,22 @@ class LayerNormFn(torch.autograd.Function):
     """nn.LayerNorm over 768 channels on an fp32 input (final encoder norm, model/modeling_slot.py:373)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, eps, out_dtype):
+    def forward(ctx, x, weight, bias, eps, out_dtype, below_scale=None):
+        """below_scale: drop-path factor [B] of the branch that consumes d(x) first (the last block's MLP branch)"""
         x = x.contiguous()
         y, mean, rstd = ops.layernorm_fwd(x, weight, bias, eps, out_dtype)
-        ctx.save_for_backward(x, mean, rstd, weight)
+        ctx.save_for_backward(x, mean, rstd, weight, below_scale)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, mean, rstd, weight = ctx.saved_tensors
-        dg, db = _flat_zeros([weight, weight], x.device)
-        dx, dxb = ops.layernorm_bwd(dy.contiguous(), x, mean, rstd, weight, dgamma=dg, dbeta=db)
-        _stash_bf16(dx, dxb)
-        return dx, dg, db, None, None
+        x, mean, rstd, weight, below = ctx.saved_tensors
+        dg, db, cs = _flat_zeros([weight, weight, weight], x.device)
+        rows_per = (x.numel() // x.shape[-1]) // below.numel() if below is not None else 1
+        dx, dxb = ops.layernorm_bwd(dy.contiguous(), x, mean, rstd, weight, dgamma=dg, dbeta=db, dx_colsum=cs, row_scale=below,
+                                    rows_per_scale=rows_per)
+        _stash_bf16(dx, dxb, below, cs)
+        return dx, dg, db, None, None, None
 
 
 # --------------------------------------------------------------------------------------------
@@ -121,7 +138,9 @@ class EncoderBlockFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, n1w, n1b, qkv_w, q_bias, v_bias, proj_w, proj_b, n2w, n2b, fc1_w, fc1_b, fc2_w, fc2_b,
-                w16, s1, s2, num_heads, eps):
+                w16, s1, s2, num_heads, eps, below_scale=None):
+        """below_scale: the MLP-branch drop-path factor of the block BELOW (the first consumer of this block's d(x)); the last
+        LayerNorm backward of this block then hands that block its scaled bf16 operand and fc2-bias gradient ready-made."""
         B, N, D = x.shape
         M = B * N
         x = x.contiguous()
@@ -137,7 +156,7 @@ class EncoderBlockFn(torch.autograd.Function):
         x2 = ops.gemm(h_act, fc216, ops.EPI_RESID_F32, bias=fc2_b, aux=x1, row_scale=s2, rows_per_scale=N)
         if need_grad:
             ctx.save_for_backward(x, mean1, rstd1, xn, attn_out, x1, mean2, rstd2, x1n, h_pre, h_act,
-                                  n1w, n2w, qkv16, proj16, fc116, fc216, s1, s2)
+                                  n1w, n2w, qkv16, proj16, fc116, fc216, s1, s2, below_scale)
             ctx.attn_state = attn_state
             ctx.dims = (B, N, D)
             ctx.shapes = [t.shape for t in (n1w, n1b, qkv_w, q_bias, v_bias, proj_w, proj_b, n2w, n2b, fc1_w, fc1_b, fc2_w, fc2_b)]
@@ -146,40 +165,44 @@ class EncoderBlockFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dx2):
         (x, mean1, rstd1, xn, attn_out, x1, mean2, rstd2, x1n, h_pre, h_act,
-         n1w, n2w, qkv16, proj16, fc116, fc216, s1, s2) = ctx.saved_tensors
+         n1w, n2w, qkv16, proj16, fc116, fc216, s1, s2, below) = ctx.saved_tensors
         B, N, D = ctx.dims
         M = B * N
         dev = dx2.device
         dx2 = dx2.contiguous()
         ours = _is_ours(dx2)   # our own LN-backward output may be updated in place along the residual chain
-        metas = [torch.empty(s, device='meta') for s in ctx.shapes]
-        (dn1w, dn1b, dqkv_w, dq_bias, dv_bias, dproj_w, dproj_b, dn2w, dn2b, dfc1_w, dfc1_b, dfc2_w, dfc2_b) = \
+        metas = [torch.empty(s, device='meta') for s in ctx.shapes] + [torch.empty(D, device='meta')]
+        (dn1w, dn1b, dqkv_w, dq_bias, dv_bias, dproj_w, dproj_b, dn2w, dn2b, dfc1_w, dfc1_b, dfc2_w, dfc2_b, below_cs) = \
             _flat_zeros(metas, dev)
         Hd = fc116.shape[0]
         # ---- MLP branch: x2 = x1 + s2 * (gelu(x1n W1^T + b1) W2^T + b2)
-        dyb = _take_bf16(dx2) if s2 is None else ops.scale_rows_cast(dx2, s2, N)
+        dyb, cs = _take_scaled(dx2, s2, N)
         dyb = dyb.view(M, D)
         dh = ops.gemm(dyb, fc216, ops.EPI_DGELU_BF16, b_mn=True, aux=h_pre)            # [M, Hd]
         ops.gemm(dyb, h_act, ops.EPI_ATOMIC_F32, a_mn=True, b_mn=True, out=dfc2_w, split_k=_wgrad_split(D, Hd, M))
-        ops.colsum_bf16(dyb, dfc2_b)
+        if cs is not None:
+            dfc2_b = cs.view(dfc2_b.shape)           # column sums came with the operand from the producing LayerNorm backward
+        else:
+            ops.colsum_bf16(dyb, dfc2_b)
         dx1n = ops.gemm(dh, fc116, ops.EPI_STORE_BF16, b_mn=True)                        # [M, D]
         ops.gemm(dh, x1n, ops.EPI_ATOMIC_F32, a_mn=True, b_mn=True, out=dfc1_w, split_k=_wgrad_split(Hd, D, M))
         ops.colsum_bf16(dh, dfc1_b)
         del dh
-        dx1, dx1b = ops.layernorm_bwd(dx1n, x1, mean2, rstd2, n2w, d_resid=dx2.view(M, D), dgamma=dn2w, dbeta=dn2b,
-                                       inplace=ours)
+        # (its bf16 copy carries this block's attention-branch factor s1, its column sums are d proj.bias)
+        dx1, dyb = ops.layernorm_bwd(dx1n, x1, mean2, rstd2, n2w, d_resid=dx2.view(M, D), dgamma=dn2w, dbeta=dn2b,
+                                      dx_colsum=dproj_b, inplace=ours, row_scale=s1, rows_per_scale=N)
         # ---- attention branch: x1 = x + s1 * (attn(xn) Wp^T + bp)
-        dyb = dx1b if s1 is None else ops.scale_rows_cast(dx1, s1, N)
         dattn = ops.gemm(dyb, proj16, ops.EPI_STORE_BF16, b_mn=True)                     # [M, D]
         ops.gemm(dyb, attn_out, ops.EPI_ATOMIC_F32, a_mn=True, b_mn=True, out=dproj_w, split_k=_wgrad_split(D, D, M))
-        ops.colsum_bf16(dyb, dproj_b)
         dqkv = _attention_bwd(ctx.attn_state, dattn)                                     # [M, 3D] bf16
         ctx.attn_state = None
         dxn = ops.gemm(dqkv, qkv16, ops.EPI_STORE_BF16, b_mn=True)                       # [M, D]
         ops.gemm(dqkv, xn.view(M, D), ops.EPI_ATOMIC_F32, a_mn=True, b_mn=True, out=dqkv_w, split_k=_wgrad_split(3 * D, D, M))
         ops.colsum_bf16(dqkv[:, :D], dq_bias)
         ops.colsum_bf16(dqkv[:, 2 * D:], dv_bias)
-        dx, dxb = ops.layernorm_bwd(dxn, x.view(M, D), mean1, rstd1, n1w, d_resid=dx1, dgamma=dn1w, dbeta=dn1b, inplace=True)
-        _stash_bf16(dx, dxb)
-        return (dx.view(B, N, D), dn1w, dn1b, dqkv_w, dq_bias, dv_bias, dproj_w, dproj_b, dn2w, dn2b, dfc1_w, dfc1_b,
-                dfc2_w, dfc2_b, None, None, None, None, None)
+        dx, dxb = ops.layernorm_bwd(dxn, x.view(M, D), mean1, rstd1, n1w, d_resid=dx1, dgamma=dn1w, dbeta=dn1b,
+                                    dx_colsum=below_cs, inplace=True, row_scale=below, rows_per_scale=N)
+        dx = dx.view(B, N, D)
+        _stash_bf16(dx, dxb.view(B, N, D), below, below_cs)
+        return (dx, dn1w, dn1b, dqkv_w, dq_bias, dv_bias, dproj_w, dproj_b, dn2w, dn2b, dfc1_w, dfc1_b,
+                dfc2_w, dfc2_b, None, None, None, None, None, None)

@@ -128,11 +128,13 @@ class Block(nn.Module):
         self.mlp = Mlp(in_features=dim, hidden_features=int(dim * mlp_ratio), act_layer=act_layer, drop=drop)
         self.gamma_1, self.gamma_2 = None, None
         self._zero_bias = None
+        self.last_scale = None
 
     def gemm_weights(self):
         return [self.attn.qkv.weight, self.attn.proj.weight, self.mlp.fc1.weight, self.mlp.fc2.weight]
 
-    def forward(self, x, return_attn=False, w16=None):
+    def forward(self, x, return_attn=False, w16=None, below_scale=None):
+        """below_scale: the MLP-branch drop-path factor of the block below (see EncoderBlockFn); `last_scale` is this block's."""
         if return_attn:
             raise NotImplementedError('return_attn=True materialises 12x1568x1568 attention maps; the fused flash path does '
                                       'not (and the reference slot model cannot run with it either, SURVEY.md R8)')
@@ -149,9 +151,10 @@ class Block(nn.Module):
             s2 = self.drop_path.row_scale(x.shape[0], x.device)
         if w16 is None:
             w16 = tuple(ops.cast_bf16(w.detach()) for w in self.gemm_weights())
+        self.last_scale = s2
         return EncoderBlockFn.apply(x, self.norm1.weight, self.norm1.bias, a.qkv.weight, qb, vb, a.proj.weight, a.proj.bias,
                                     self.norm2.weight, self.norm2.bias, self.mlp.fc1.weight, self.mlp.fc1.bias,
-                                    self.mlp.fc2.weight, self.mlp.fc2.bias, w16, s1, s2, a.num_heads, self.norm1.eps)
+                                    self.mlp.fc2.weight, self.mlp.fc2.bias, w16, s1, s2, a.num_heads, self.norm1.eps, below_scale)
 
 
 class PatchEmbed(nn.Module):
@@ -371,9 +374,11 @@ class VisionTransformer(nn.Module):
                 x = self.patch_embed(x, pos_table=None, w16=pe16) + self.pos_embed
             else:
                 x = self.patch_embed(x, pos_table=pos, w16=pe16)
+            below = None          # drop-path factor of the consumer of each block's input gradient (fused into its LN backward)
             for blk, w16 in zip(self.blocks, blk16):
-                x = blk(x, w16=w16)
-            return LayerNormFn.apply(x, self.norm.weight, self.norm.bias, self.norm.eps, self.token_dtype)
+                x = blk(x, w16=w16, below_scale=below)
+                below = blk.last_scale
+            return LayerNormFn.apply(x, self.norm.weight, self.norm.bias, self.norm.eps, self.token_dtype, below)
 
     def _head_linear(self, x):
         if isinstance(self.head, nn.Linear) and x.dtype == torch.float32:

@@ -76,9 +76,10 @@ def layernorm_fwd(x: torch.Tensor, gamma, beta, eps: float, out_dtype=torch.bflo
 
 
 def layernorm_bwd(dy, x, mean, rstd, gamma, d_resid=None, want_dx=True, want_bf16=True, dgamma=None, dbeta=None,
-                  dx_colsum=None, inplace=False):
+                  dx_colsum=None, inplace=False, row_scale=None, rows_per_scale=1):
     """returns (dx fp32 | None, dx bf16 | None); dgamma/dbeta/dx_colsum are accumulated in place when given.
-    inplace=True writes dx over d_resid (only for gradient buffers this package produced itself)."""
+    inplace=True writes dx over d_resid (only for gradient buffers this package produced itself).
+    row_scale [rows / rows_per_scale] multiplies the bf16 copy and dx_colsum (the consumer's drop-path factor), not dx."""
     _need_cuda(dy, x)
     assert dy.is_contiguous() and x.is_contiguous() and dy.dtype in (torch.bfloat16, torch.float32)
     D = x.shape[-1]
@@ -91,7 +92,7 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, d_resid=None, want_dx=True, want_bf1
     dxb = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16) if want_bf16 else None
     rc = _lib.lib().devias_layernorm_bwd(dy.data_ptr(), int(dy.dtype == torch.bfloat16), x.data_ptr(), mean.data_ptr(),
                                          rstd.data_ptr(), gamma.data_ptr(), _ptr(d_resid), _ptr(dx), _ptr(dxb), _ptr(dgamma),
-                                         _ptr(dbeta), _ptr(dx_colsum), rows, D, _stream())
+                                         _ptr(dbeta), _ptr(dx_colsum), _ptr(row_scale), int(rows_per_scale), rows, D, _stream())
     _lib.check(rc, 'layernorm_bwd')
     return dx, dxb
 

@@ -109,12 +109,14 @@ int devias_slot_stream_bwd(const float* tokens, const float* mu, const float* rs
  * agg_block/attention.py:29-30 (eps 1e-5).
  * Backward: dx = d_resid + dLN(dy) (fp32, optional) and/or its bf16 copy; dgamma/dbeta/dx_colsum (fp32 [dim], optional)
  * are ACCUMULATED (+=).  d_resid may be NULL; dx may alias d_resid.  dx_colsum = column sums of dx, i.e. the bias
- * gradient of the linear layer that produced the residual branch (Block.forward, model/modeling_slot.py:150-151). */
+ * gradient of the linear layer that produced the residual branch (Block.forward, model/modeling_slot.py:150-151).
+ * bf16_row_scale (optional, [rows / rows_per_scale]): the per-sample drop-path factor (modeling_slot.py:36-47) of the branch
+ * that consumes this gradient next; it multiplies the bf16 copy and dx_colsum only (dx itself stays unscaled). */
 int devias_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y, int y_is_bf16, float* mean,
                          float* rstd, int rows, int dim, float eps, void* stream);
 int devias_layernorm_bwd(const void* dy, int dy_is_bf16, const float* x, const float* mean, const float* rstd,
                          const float* gamma, const float* d_resid, float* dx, void* dx_bf16, float* dgamma, float* dbeta,
-                         float* dx_colsum, int rows, int dim, void* stream);
+                         float* dx_colsum, const float* bf16_row_scale, int rows_per_scale, int rows, int dim, void* stream);
 /* out[c] += sum_r a[r, c]  (bf16 [rows, cols] with row stride lda) -- bias gradients of qkv / fc1 */
 int devias_colsum_bf16(const void* a, int64_t lda, int rows, int cols, float* out, void* stream);
 
