@@ -12,6 +12,6 @@ def attention_fwd(qkv: torch.Tensor, B: int, N: int, H: int, need_grad: bool):
     return out, ((qkv, out, lse2, B, N, H) if need_grad else None)
 
 
-def attention_bwd(state, dout: torch.Tensor) -> torch.Tensor:
+def attention_bwd(state, dout: torch.Tensor, delta=None) -> torch.Tensor:
     qkv, out, lse2, B, N, H = state
-    return ops.flash_attn_bwd(qkv, out, dout.contiguous(), lse2, B, N, H)
+    return ops.flash_attn_bwd(qkv, out, dout.contiguous(), lse2, B, N, H, delta=delta)

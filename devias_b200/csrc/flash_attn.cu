@@ -839,7 +839,7 @@ extern "C" int devias_flash_attn_fwd(const void* qkv, void* out, float* lse2, in
 
 extern "C" int devias_flash_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse2, void* dqkv,
                                      float* delta_ws, float* dq_ws, int batch, int seq, int heads, int head_dim, float scale,
-                                     void* stream) {
+                                     int delta_ready, void* stream) {
   using namespace dv;
   DV_REQUIRE(qkv && out && dout && lse2 && dqkv && delta_ws && dq_ws, "null pointer");
   DV_REQUIRE(head_dim == 64, "head_dim 64 only (ViT-B/16)");
@@ -865,7 +865,7 @@ extern "C" int devias_flash_attn_bwd(const void* qkv, const void* out, const voi
     attr_done = true;
   }
   DV_CHECK_CUDA(cudaMemsetAsync(dq_ws, 0, (size_t)batch * seq * D * sizeof(float), s));
-  {
+  if (!delta_ready) {
     const long long total = (long long)batch * Npad * heads;
     flash_delta_kernel<<<(int)((total + 255) / 256), 256, 0, s>>>(static_cast<const __nv_bfloat16*>(out),
                                                                   static_cast<const __nv_bfloat16*>(dout), delta_ws, batch, seq,

@@ -127,9 +127,9 @@ def _attention_fwd(qkv, B, N, H, need_grad):
     return attention.attention_fwd(qkv, B, N, H, need_grad)
 
 
-def _attention_bwd(state, dout):
+def _attention_bwd(state, dout, delta=None):
     from . import attention
-    return attention.attention_bwd(state, dout)
+    return attention.attention_bwd(state, dout, delta)
 
 
 class EncoderBlockFn(torch.autograd.Function):
@@ -192,6 +192,8 @@ class EncoderBlockFn(torch.autograd.Function):
         dx1, dyb = ops.layernorm_bwd(dx1n, x1, mean2, rstd2, n2w, d_resid=dx2.view(M, D), dgamma=dn2w, dbeta=dn2b,
                                       dx_colsum=dproj_b, inplace=ours, row_scale=s1, rows_per_scale=N)
         # ---- attention branch: x1 = x + s1 * (attn(xn) Wp^T + bp)
+        # (ops.gemm_dgrad_delta can produce the flash backward's row term in this GEMM's epilogue; measured slower than the
+        #  stand-alone 15 us kernel because this K = 768 GEMM is epilogue-bound: 14.40 vs 14.26 ms per step)
         dattn = ops.gemm(dyb, proj16, ops.EPI_STORE_BF16, b_mn=True)                     # [M, D]
         ops.gemm(dyb, attn_out, ops.EPI_ATOMIC_F32, a_mn=True, b_mn=True, out=dproj_w, split_k=_wgrad_split(D, D, M))
         dqkv = _attention_bwd(ctx.attn_state, dattn)                                     # [M, 3D] bf16

@@ -61,6 +61,7 @@ int devias_profile_end(int kind, double* total_ms, double* total_work, int64_t* 
 #define DEVIAS_EPI_DGELU_BF16 3
 #define DEVIAS_EPI_RESID_F32 4
 #define DEVIAS_EPI_ATOMIC_F32 5
+#define DEVIAS_EPI_DELTA_BF16 6 /* internal to devias_gemm_dgrad_delta */
 int devias_gemm_bf16(const void* a, int64_t lda, int a_mn_major, const void* b, int64_t ldb, int b_mn_major, int m, int n,
                      int k, int epilogue, void* out, int64_t ldo, void* out2, int64_t ldo2, const float* bias,
                      const void* aux, int64_t ldaux, int aux_row_mod, const float* row_scale, int rows_per_scale,
@@ -77,7 +78,16 @@ int devias_gemm_bf16(const void* a, int64_t lda, int a_mn_major, const void* b, 
 int devias_flash_attn_fwd(const void* qkv, void* out, float* lse2, int batch, int seq, int heads, int head_dim, float scale,
                           void* stream);
 int devias_flash_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse2, void* dqkv, float* delta_ws,
-                          float* dq_ws, int batch, int seq, int heads, int head_dim, float scale, void* stream);
+                          float* dq_ws, int batch, int seq, int heads, int head_dim, float scale, int delta_ready, void* stream);
+/* delta_ready != 0: delta_ws already holds delta[b, h, q] = sum_d dout * out (rows q >= seq finite), e.g. from
+ * devias_gemm_dgrad_delta below, and is not recomputed.
+ *
+ * dout = dy w (input gradient of Attention.proj, model/modeling_slot.py:113; w [n, k] row-major read mn-major, or [k, n] with
+ * w_mn_major = 0) with delta produced in the same epilogue: n = heads * 64, m = batch * seq rows, o_fwd = the forward
+ * attention output [m, n] bf16, delta fp32 [batch * heads * npad]. */
+int devias_gemm_dgrad_delta(const void* dy, int64_t ld_dy, const void* w, int64_t ldw, int w_mn_major, int m, int n, int k,
+                            void* dout, int64_t ld_dout, const void* o_fwd, int64_t ld_o, float* delta, int seq, int npad,
+                            int heads, void* stream);
 
 /* ---- streaming slot attention (folded form; devias_b200/slot_attention.py) ----------------------------
  * One pass over the context tokens of every clip, replacing per layer: LayerNorm(context) + to_k + to_v + q k^T + slot-axis

@@ -162,3 +162,47 @@ def test_teacher_bf16_vs_golden():
     assert_close(tok, g['token'], E2E_TOL, 'teacher token')
     assert_close(logit, g['logits'], E2E_TOL, 'teacher logits')
     assert int(logit.argmax()) == int(g['logits'].argmax())
+
+
+def test_drop_path_scales_forward_and_gradients():
+    """Per-sample drop-path factors (model/modeling_slot.py:36-47) travel fused through the residual epilogues (forward) and the
+    LayerNorm-backward bf16 copies / bias column sums (backward): two encoder blocks + final norm with FIXED factors against
+    an fp32 restatement built from the oracle's attention / MLP."""
+    import torch.nn.functional as F
+    from functools import partial
+    from devias_b200.modeling_slot import VisionTransformer, DropPath
+    B, depth = 3, 2
+    sd = O.synth_state_dict(num_classes=101, num_latents=2, agg_depth=4, agg_weights_tie=True, depth=depth, seed=21)
+    m = _quiet(VisionTransformer, patch_size=16, embed_dim=768, depth=depth, num_heads=12, mlp_ratio=4, qkv_bias=True,
+               norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), num_classes=101, num_latents=2, agg_depth=4,
+               agg_weights_tie=True, slot_matching_method='matching', init_scale=1.0, drop_path_rate=0.5)
+    m.load_state_dict(sd)
+    m = m.cuda().train()
+    scales = [torch.tensor(v, device='cuda') for v in ([2.0, 0.0, 1.0], [0.0, 2.0, 2.0], [1.0, 1.0, 0.0], [2.0, 2.0, 0.0])]
+    it = iter(scales)
+    orig = DropPath.row_scale
+    DropPath.row_scale = lambda self, batch, device: next(it)
+    try:
+        for b in m.blocks:                         # block 0 has rate 0 (nn.Identity): give both blocks a DropPath
+            b.drop_path = DropPath(0.5)
+        x = O.synth_clips(B, seed=9).cuda()
+        tokens = m.forward_features(x)
+        w = MG.probe_weights([tuple(tokens.shape)], seed=3)[0]
+        (tokens * w.cuda()).sum().backward()
+    finally:
+        DropPath.row_scale = orig
+    # fp32 restatement with the same factors
+    osd = {k: v.clone().requires_grad_(True) for k, v in sd.items() if k.startswith(('blocks.', 'norm.', 'patch_embed.'))}
+    t = O.patch_embed(osd, O.synth_clips(B, seed=9)) + O.sinusoid_table(1568, 768)
+    sc = [s.cpu().view(B, 1, 1) for s in scales]
+    for i in range(depth):
+        p = f'blocks.{i}.'
+        t = t + sc[2 * i] * O.encoder_attention(osd, p + 'attn.', F.layer_norm(t, (768,), osd[p + 'norm1.weight'], osd[p + 'norm1.bias'], 1e-6))
+        t = t + sc[2 * i + 1] * O.encoder_mlp(osd, p + 'mlp.', F.layer_norm(t, (768,), osd[p + 'norm2.weight'], osd[p + 'norm2.bias'], 1e-6))
+    ref = F.layer_norm(t, (768,), osd['norm.weight'], osd['norm.bias'], 1e-6)
+    (ref * w).sum().backward()
+    assert_close(tokens, ref, E2E_TOL, 'tokens with drop-path factors')
+    own = dict(m.named_parameters())
+    for k in ('blocks.1.mlp.fc2.bias', 'blocks.1.mlp.fc2.weight', 'blocks.0.mlp.fc2.bias', 'blocks.0.attn.proj.bias',
+              'blocks.1.attn.proj.bias', 'blocks.0.attn.qkv.weight', 'blocks.0.norm1.weight', 'patch_embed.proj.bias'):
+        assert_close(own[k].grad, osd[k].grad, 3e-2, 'grad ' + k)
