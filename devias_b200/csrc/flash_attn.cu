@@ -428,9 +428,10 @@ flash_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             const float x0 = (!RAGGED || 16 * c + 2 * i < valid) ? __uint_as_float(cur[2 * i]) : -INFINITY;
             const float x1 = (!RAGGED || 16 * c + 2 * i + 1 < valid) ? __uint_as_float(cur[2 * i + 1]) : -INFINITY;
             const uint64_t y = f2_fma(f2_pack(x0, x1), cc, negm);
-            const float e0 = fast_exp2(f2_lo(y)), e1 = fast_exp2(f2_hi(y));
-            sum2 = f2_add(sum2, f2_pack(e0, e1));
-            pk[i] = pack_bf16(e0, e1);
+            // three of every eight pairs take the polynomial path on the FMA pipe, the rest MUFU.EX2 (ncu: XU 67 % busy)
+            const uint64_t ev = (i == 1 || i == 4 || i == 6) ? exp2_poly_pair(y) : f2_pack(fast_exp2(f2_lo(y)), fast_exp2(f2_hi(y)));
+            sum2 = f2_add(sum2, ev);
+            pk[i] = pack_bf16(f2_lo(ev), f2_hi(ev));
           }
           tmem_st_32x32b_x8(tm_s + lane_sel + 8 * c, pk);
         }

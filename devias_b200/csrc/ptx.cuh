@@ -392,6 +392,22 @@ __device__ __forceinline__ float fast_exp2(float x) {  // MUFU.EX2; exp2(-inf) =
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// exp2 of a packed pair on the FMA / ALU pipes (no MUFU): Cody-Waite split by the 1.5 * 2^23 rounding trick + cubic minimax
+// polynomial of 2^f on [-0.5, 0.5] (max relative error 7.5e-5, far below bf16 resolution), exponent added with a shift.
+// Inputs are clamped at -126 (exp2(-inf) -> 2^-126 ~ 1e-38 instead of 0).  The flash-attention forward sends part of its
+// exponentials through here because MUFU.EX2 (16 per clock and SM) is what bounds it at head_dim 64.
+__device__ __forceinline__ uint64_t exp2_poly_pair(uint64_t y) {
+  const uint64_t yc = f2_pack(fmaxf(f2_lo(y), -126.0f), fmaxf(f2_hi(y), -126.0f));
+  const uint64_t t = f2_add(yc, f2_pack(12582912.0f, 12582912.0f));
+  const uint64_t xi = f2_add(t, f2_pack(-12582912.0f, -12582912.0f));
+  const uint64_t xf = f2_fma(xi, f2_pack(-1.0f, -1.0f), yc);
+  uint64_t p = f2_fma(f2_pack(0.0551716685f, 0.0551716685f), xf, f2_pack(0.2426111251f, 0.2426111251f));
+  p = f2_fma(p, xf, f2_pack(0.6932609677f, 0.6932609677f));
+  p = f2_fma(p, xf, f2_pack(0.9999280572f, 0.9999280572f));
+  const uint32_t r0 = __float_as_uint(f2_lo(p)) + (__float_as_uint(f2_lo(t)) << 23);
+  const uint32_t r1 = __float_as_uint(f2_hi(p)) + (__float_as_uint(f2_hi(t)) << 23);
+  return f2_pack(__uint_as_float(r0), __uint_as_float(r1));
+}
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
   const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
