@@ -46,6 +46,7 @@ def parse():
     ap.add_argument('--batch', type=int, default=0, help='clips per GPU (default: the workload recipe)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--split-block', type=int, default=3, help='data-parallel step: encoder block at which the backward graph is cut')
     ap.add_argument('--no-graph', action='store_true', help='eager launches instead of the captured CUDA graph')
     return ap.parse_args()
 
@@ -227,7 +228,7 @@ def main():
     barrier()
     graphed = None
     if use_graph:
-        graphed = engine.GraphedTrainStep(model, crit, opt, devb, reducer=reducer, warmup=1)
+        graphed = engine.GraphedTrainStep(model, crit, opt, devb, reducer=reducer, warmup=1, split_block=args.split_block)
         for i in range(2):
             graphed(i % nbuf)
         barrier()
