@@ -153,7 +153,10 @@ def run_reference(args, cfg):
         'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'clips/s', 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': f'{args.workload}: DEVIAS ViT-B/16 + {cfg["num_latents"]}-slot agg depth {cfg["agg_depth"]} train step, CPU', 'clips_per_step': 1},
+        'config': {'workload': f'{args.workload}: DEVIAS ViT-B/16 (1568 tube tokens) + {cfg["num_latents"]}-slot aggregation, '
+                               f'tied={cfg["agg_weights_tie"]} depth {cfg["agg_depth"]}, {cfg["num_classes"]}+365 classes, train step '
+                               f'(fwd + TrainLoss + bwd), reference CPU path (oracle port), bounded sample of 1 clip per step',
+                   'clips_per_step': 1, 'parallelism': 'cpu'},
         'cpu_baseline': {'value': v, 'unit': 'clips/s', 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': v, 'unit': 'clips/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
