@@ -19,6 +19,15 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+# small public aliases for modules that bind further entry points themselves (slot_linear.py)
+stream = _stream
+check = _lib.check
+
+
+def L():
+    return _lib.lib()
+
+
 def _need_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:

@@ -57,13 +57,16 @@ def slot_attention_layer(x, tokens, mu, r, p, stream=slot_stream_torch, lin=None
     q = linear(xn, p['wq']).view(B, S, H, dh)
     if lin is None:
         qt = torch.einsum('bshd,hdc->bhsc', q, p['wk'].view(H, dh, D)) * (dh ** -0.5)     # [B,H,S,D]
+        g = (qt * p['ctx_w']).reshape(B, H * S, D)
+        G = g.sum(-1)
+        c0 = (qt @ p['ctx_b']).reshape(B, H * S)
     else:
-        qt = lin.fold_keys(q, p['wk']) * (dh ** -0.5)
-    g = (qt * p['ctx_w']).reshape(B, H * S, D)
-    G = g.sum(-1)
-    c0 = (qt @ p['ctx_b']).reshape(B, H * S)
+        g, G, c0 = lin.fold_epilogue(lin.fold_keys(q, p['wk']), p['ctx_w'], p['ctx_b'], dh ** -0.5)
     U, m, A, a = stream(tokens, mu, r, g.contiguous(), G.contiguous(), c0.contiguous(), **stream_kw)
-    cbar = (p['ctx_w'] * (U - m.unsqueeze(-1)) + p['ctx_b'] * A.unsqueeze(-1)) / (A.unsqueeze(-1) + 1e-7)
+    if lin is None:
+        cbar = (p['ctx_w'] * (U - m.unsqueeze(-1)) + p['ctx_b'] * A.unsqueeze(-1)) / (A.unsqueeze(-1) + 1e-7)
+    else:
+        cbar = lin.context(U, m, A, p['ctx_w'], p['ctx_b'], 1e-7)
     if lin is None:
         out = torch.einsum('bhsc,hdc->bshd', cbar.view(B, H, S, D), p['wv'].view(H, dh, D)).reshape(B, S, H * dh)
     else:

@@ -115,3 +115,76 @@ def apply_values(cbar, wv):
     if B * S > MAX_ROWS:
         return torch.einsum('bhsc,hdc->bshd', cbar, wv.view(H, -1, D)).reshape(B, S, -1)
     return _ApplyValuesFn.apply(cbar, wv)
+
+
+# --------------------------------------------------------------------------------------------
+# the O(S) algebra around the streaming kernel (csrc/slot_glue.cu): one launch per direction instead of ~15 elementwise /
+# reduction launches each
+class _FoldEpilogueFn(torch.autograd.Function):
+    """(qt [B,H,S,D], gamma, beta, scale) -> g [B,H*S,D] = scale qt gamma, G [B,H*S] = sum_c g, c0 [B,H*S] = scale qt . beta"""
+
+    @staticmethod
+    def forward(ctx, qt, gamma, beta, scale):
+        B, H, S, D = qt.shape
+        qt, gamma, beta = qt.contiguous(), gamma.contiguous(), beta.contiguous()
+        R = B * H * S
+        g = torch.empty(B, H * S, D, device=qt.device, dtype=torch.float32)
+        G = torch.empty(B, H * S, device=qt.device, dtype=torch.float32)
+        c0 = torch.empty(B, H * S, device=qt.device, dtype=torch.float32)
+        ops.check(ops.L().devias_slot_fold_fwd(qt.data_ptr(), gamma.data_ptr(), beta.data_ptr(), float(scale), g.data_ptr(),
+                                               G.data_ptr(), c0.data_ptr(), R, D, ops.stream()), 'slot_fold_fwd')
+        ctx.save_for_backward(qt, gamma, beta)
+        ctx.scale = float(scale)
+        return g, G, c0
+
+    @staticmethod
+    def backward(ctx, dg, dG, dc0):
+        qt, gamma, beta = ctx.saved_tensors
+        B, H, S, D = qt.shape
+        R = B * H * S
+        z = lambda ref_shape: torch.zeros(ref_shape, device=qt.device, dtype=torch.float32)
+        dg = z((B, H * S, D)) if dg is None else dg.contiguous()
+        dG = z((B, H * S)) if dG is None else dG.contiguous()
+        dc0 = z((B, H * S)) if dc0 is None else dc0.contiguous()
+        dqt = torch.empty_like(qt)
+        dgb = torch.zeros(2, D, device=qt.device, dtype=torch.float32)
+        ops.check(ops.L().devias_slot_fold_bwd(qt.data_ptr(), gamma.data_ptr(), beta.data_ptr(), ctx.scale, dg.data_ptr(), dG.data_ptr(),
+                                               dc0.data_ptr(), dqt.data_ptr(), dgb[0].data_ptr(), dgb[1].data_ptr(), R, D, ops.stream()),
+                  'slot_fold_bwd')
+        return dqt, dgb[0], dgb[1], None
+
+
+class _ContextFn(torch.autograd.Function):
+    """cbar = (gamma (U - m) + beta A) / (A + eps);  U [B,HS,D], m, A [B,HS]"""
+
+    @staticmethod
+    def forward(ctx, U, m, A, gamma, beta, eps):
+        U, m, A, gamma, beta = U.contiguous(), m.contiguous(), A.contiguous(), gamma.contiguous(), beta.contiguous()
+        B, HS, D = U.shape
+        cbar = torch.empty_like(U)
+        ops.check(ops.L().devias_slot_ctx_fwd(U.data_ptr(), m.data_ptr(), A.data_ptr(), gamma.data_ptr(), beta.data_ptr(), float(eps),
+                                              cbar.data_ptr(), B * HS, D, ops.stream()), 'slot_ctx_fwd')
+        ctx.save_for_backward(U, m, A, gamma, beta)
+        ctx.eps = float(eps)
+        return cbar
+
+    @staticmethod
+    def backward(ctx, dcbar):
+        U, m, A, gamma, beta = ctx.saved_tensors
+        B, HS, D = U.shape
+        dcbar = dcbar.contiguous()
+        dU = torch.empty_like(U)
+        dmA = torch.empty(2, B, HS, device=U.device, dtype=torch.float32)
+        dgb = torch.zeros(2, D, device=U.device, dtype=torch.float32)
+        ops.check(ops.L().devias_slot_ctx_bwd(dcbar.data_ptr(), U.data_ptr(), m.data_ptr(), A.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                              ctx.eps, dU.data_ptr(), dmA[0].data_ptr(), dmA[1].data_ptr(), dgb[0].data_ptr(),
+                                              dgb[1].data_ptr(), B * HS, D, ops.stream()), 'slot_ctx_bwd')
+        return dU, dmA[0], dmA[1], dgb[0], dgb[1], None
+
+
+def fold_epilogue(qt, gamma, beta, scale):
+    return _FoldEpilogueFn.apply(qt, gamma, beta, scale)
+
+
+def context(U, m, A, gamma, beta, eps=1e-7):
+    return _ContextFn.apply(U, m, A, gamma, beta, eps)

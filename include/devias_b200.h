@@ -141,6 +141,20 @@ int devias_scale_rows_cast(const float* in, void* out, int rows, int cols, const
                            void* stream);
 int devias_patchify(const void* clip, int clip_dtype, void* out, int batch, int chans, int frames, int height, int width,
                     void* stream);
+/* ---- slot-side glue around the streaming kernel (devias_b200/slot_attention.py), rows = batch * 4 * slots, dim = 768 --------
+ * fold : g = scale * qt * gamma,  G[r] = sum_c g[r, c],  c0[r] = scale * sum_c qt[r, c] * beta[c]   (qt = Wk_h^T q: the key projection
+ *        and the context LayerNorm's affine folded onto the slot queries, agg_block/attention.py:35-38,121-131)
+ * ctx  : cbar = (gamma * (U - m) + beta * A) / (A + eps)   (token-axis renormalised context before to_v, :132-136)
+ * The backward entry points ACCUMULATE (+=) into dgamma / dbeta. */
+int devias_slot_fold_fwd(const float* qt, const float* gamma, const float* beta, float scale, float* g, float* G, float* c0, int rows,
+                         int dim, void* stream);
+int devias_slot_fold_bwd(const float* qt, const float* gamma, const float* beta, float scale, const float* dg, const float* dG,
+                         const float* dc0, float* dqt, float* dgamma, float* dbeta, int rows, int dim, void* stream);
+int devias_slot_ctx_fwd(const float* U, const float* m, const float* A, const float* gamma, const float* beta, float eps, float* cbar,
+                        int rows, int dim, void* stream);
+int devias_slot_ctx_bwd(const float* dcbar, const float* U, const float* m, const float* A, const float* gamma, const float* beta,
+                        float eps, float* dU, float* dm, float* dA, float* dgamma, float* dbeta, int rows, int dim, void* stream);
+
 /* ---- head: slot selection (model/modeling_slot.py:396-404; model/modeling_slot_fusion.py:376-386) -------------
  * logits [batch*slots, ld] fp32 (n_action + n_scene used columns) -> per clip the slot whose softmax row has the largest
  * action-class probability / scene-class probability (int64 [batch] each; first maximum wins, as torch.argmax). */

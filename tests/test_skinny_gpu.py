@@ -63,3 +63,39 @@ def test_fold_keys_and_apply_values(B, S):
     ref = torch.einsum('bhsc,hdc->bshd', cd, vd.view(H, dh, D)).reshape(B, S, H * dh)
     rc, rv = torch.autograd.grad(ref, [cd, vd], dout.double())
     assert _rel(out, ref) < 2e-6 and _rel(gc, rc) < 2e-6 and _rel(gv, rv) < 2e-6
+
+
+@pytest.mark.parametrize('B,S', [(8, 2), (1, 2), (5, 4), (3, 8)])
+def test_fold_epilogue_and_context_match_torch(B, S):
+    """csrc/slot_glue.cu against the torch expressions of devias_b200/slot_attention.py, values and every gradient (fp64 reference)"""
+    from devias_b200 import slot_linear
+    H, D = 4, 768
+    g_ = torch.Generator(device='cuda').manual_seed(B * 13 + S)
+    rnd = lambda *s: torch.randn(*s, device='cuda', generator=g_)
+    qt = rnd(B, H, S, D).requires_grad_(True)
+    gamma = (1 + 0.1 * rnd(D)).requires_grad_(True)
+    beta = (0.05 * rnd(D)).requires_grad_(True)
+    scale = 512 ** -0.5
+    g, G, c0 = slot_linear.fold_epilogue(qt, gamma, beta, scale)
+    wg, wG, wc = rnd(B, H * S, D), rnd(B, H * S), rnd(B, H * S)
+    grads = torch.autograd.grad((g * wg).sum() + (G * wG).sum() + (c0 * wc).sum(), [qt, gamma, beta])
+    qd, gd, bd = (t.detach().double().requires_grad_(True) for t in (qt, gamma, beta))
+    q2 = qd * scale
+    rg = (q2 * gd).reshape(B, H * S, D); rG = rg.sum(-1); rc = (q2 @ bd).reshape(B, H * S)
+    rgrads = torch.autograd.grad((rg * wg.double()).sum() + (rG * wG.double()).sum() + (rc * wc.double()).sum(), [qd, gd, bd])
+    assert _rel(g, rg) < 2e-6 and _rel(G, rG) < 2e-6 and _rel(c0, rc) < 2e-6
+    for a, r in zip(grads, rgrads):
+        assert _rel(a, r) < 5e-6
+
+    U = rnd(B, H * S, D).requires_grad_(True)
+    m = rnd(B, H * S).requires_grad_(True)
+    A = (rnd(B, H * S).abs() * 50 + 1).requires_grad_(True)
+    cbar = slot_linear.context(U, m, A, gamma, beta, 1e-7)
+    wcb = rnd(B, H * S, D)
+    grads = torch.autograd.grad((cbar * wcb).sum(), [U, m, A, gamma, beta])
+    Ud, md, Ad = (t.detach().double().requires_grad_(True) for t in (U, m, A))
+    ref = (gd * (Ud - md.unsqueeze(-1)) + bd * Ad.unsqueeze(-1)) / (Ad.unsqueeze(-1) + 1e-7)
+    rgrads = torch.autograd.grad((ref * wcb.double()).sum(), [Ud, md, Ad, gd, bd])
+    assert _rel(cbar, ref) < 2e-6
+    for a, r in zip(grads, rgrads):
+        assert _rel(a, r) < 5e-6
