@@ -133,8 +133,9 @@ class Block(nn.Module):
     def gemm_weights(self):
         return [self.attn.qkv.weight, self.attn.proj.weight, self.mlp.fc1.weight, self.mlp.fc2.weight]
 
-    def forward(self, x, return_attn=False, w16=None, below_scale=None):
-        """below_scale: the MLP-branch drop-path factor of the block below (see EncoderBlockFn); `last_scale` is this block's."""
+    def forward(self, x, return_attn=False, w16=None, below_scale=None, scales=None):
+        """below_scale: the MLP-branch drop-path factor of the block below (see EncoderBlockFn); `last_scale` is this block's.
+        scales: (s1, s2) drop-path factors drawn by the caller for the whole encoder at once (else drawn here)."""
         if return_attn:
             raise NotImplementedError('return_attn=True materialises 12x1568x1568 attention maps; the fused flash path does '
                                       'not (and the reference slot model cannot run with it either, SURVEY.md R8)')
@@ -146,7 +147,9 @@ class Block(nn.Module):
         else:
             qb, vb = a.q_bias, a.v_bias
         s1 = s2 = None
-        if isinstance(self.drop_path, DropPath):
+        if scales is not None:
+            s1, s2 = scales
+        elif isinstance(self.drop_path, DropPath):
             s1 = self.drop_path.row_scale(x.shape[0], x.device)
             s2 = self.drop_path.row_scale(x.shape[0], x.device)
         if w16 is None:
@@ -354,6 +357,22 @@ class VisionTransformer(nn.Module):
         v = self._arena.views16
         return v[0], [tuple(v[1 + 4 * i: 5 + 4 * i]) for i in range(len(self.blocks))]
 
+    def _draw_drop_path(self, batch, device):
+        """Per-sample stochastic-depth factors floor(keep + U) / keep (model/modeling_slot.py:36-47) of ALL blocks and both
+        branches in three launches instead of six per block; returns [(s1, s2)] per block (None where the rate is 0)."""
+        if not self.training:
+            return None
+        rates = [float(getattr(b.drop_path, 'drop_prob', 0.0) or 0.0) for b in self.blocks]
+        if not any(r > 0 for r in rates):
+            return None
+        key = (tuple(rates), str(device))
+        if getattr(self, '_dp_keep', None) is None or self._dp_keep[0] != key:
+            keep = torch.tensor([1.0 - r for r in rates for _ in range(2)], device=device, dtype=torch.float32).unsqueeze(1)
+            self._dp_keep = (key, keep)
+        keep = self._dp_keep[1]
+        s = torch.floor(keep + torch.rand(keep.shape[0], batch, device=device, dtype=torch.float32)) / keep
+        return [(s[2 * i], s[2 * i + 1]) if r > 0 else (None, None) for i, r in enumerate(rates)]
+
     def _pos_table(self, device):
         pe = self.pos_embed
         if isinstance(pe, nn.Parameter):
@@ -375,8 +394,9 @@ class VisionTransformer(nn.Module):
             else:
                 x = self.patch_embed(x, pos_table=pos, w16=pe16)
             below = None          # drop-path factor of the consumer of each block's input gradient (fused into its LN backward)
-            for blk, w16 in zip(self.blocks, blk16):
-                x = blk(x, w16=w16, below_scale=below)
+            all_scales = self._draw_drop_path(x.shape[0], x.device)
+            for i, (blk, w16) in enumerate(zip(self.blocks, blk16)):
+                x = blk(x, w16=w16, below_scale=below, scales=None if all_scales is None else all_scales[i])
                 below = blk.last_scale
             return LayerNormFn.apply(x, self.norm.weight, self.norm.bias, self.norm.eps, self.token_dtype, below)
 

@@ -179,18 +179,11 @@ def test_drop_path_scales_forward_and_gradients():
     m.load_state_dict(sd)
     m = m.cuda().train()
     scales = [torch.tensor(v, device='cuda') for v in ([2.0, 0.0, 1.0], [0.0, 2.0, 2.0], [1.0, 1.0, 0.0], [2.0, 2.0, 0.0])]
-    it = iter(scales)
-    orig = DropPath.row_scale
-    DropPath.row_scale = lambda self, batch, device: next(it)
-    try:
-        for b in m.blocks:                         # block 0 has rate 0 (nn.Identity): give both blocks a DropPath
-            b.drop_path = DropPath(0.5)
-        x = O.synth_clips(B, seed=9).cuda()
-        tokens = m.forward_features(x)
-        w = MG.probe_weights([tuple(tokens.shape)], seed=3)[0]
-        (tokens * w.cuda()).sum().backward()
-    finally:
-        DropPath.row_scale = orig
+    m._draw_drop_path = lambda batch, device: [(scales[0], scales[1]), (scales[2], scales[3])]   # fixed factors instead of random draws
+    x = O.synth_clips(B, seed=9).cuda()
+    tokens = m.forward_features(x)
+    w = MG.probe_weights([tuple(tokens.shape)], seed=3)[0]
+    (tokens * w.cuda()).sum().backward()
     # fp32 restatement with the same factors
     osd = {k: v.clone().requires_grad_(True) for k, v in sd.items() if k.startswith(('blocks.', 'norm.', 'patch_embed.'))}
     t = O.patch_embed(osd, O.synth_clips(B, seed=9)) + O.sinusoid_table(1568, 768)
@@ -206,3 +199,23 @@ def test_drop_path_scales_forward_and_gradients():
     for k in ('blocks.1.mlp.fc2.bias', 'blocks.1.mlp.fc2.weight', 'blocks.0.mlp.fc2.bias', 'blocks.0.attn.proj.bias',
               'blocks.1.attn.proj.bias', 'blocks.0.attn.qkv.weight', 'blocks.0.norm1.weight', 'patch_embed.proj.bias'):
         assert_close(own[k].grad, osd[k].grad, 3e-2, 'grad ' + k)
+
+
+def test_batched_drop_path_draw_statistics():
+    """all blocks' stochastic-depth factors in one draw: values in {0, 1/keep}, mean ~ 1, None for rate-0 blocks and in eval mode"""
+    from functools import partial
+    from devias_b200.modeling_slot import VisionTransformer
+    m = _quiet(VisionTransformer, patch_size=16, embed_dim=768, depth=3, num_heads=12, mlp_ratio=4, qkv_bias=True,
+               norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), num_classes=101, num_latents=2, agg_depth=1,
+               agg_weights_tie=True, slot_matching_method='matching', drop_path_rate=0.4).cuda().train()
+    torch.manual_seed(0)
+    sc = m._draw_drop_path(4096, torch.device('cuda'))
+    assert sc[0] == (None, None)                                  # linspace(0, 0.4, 3)[0] = 0
+    for i, rate in ((1, 0.2), (2, 0.4)):
+        for s in sc[i]:
+            keep = 1.0 - rate
+            vals = torch.unique(s)
+            assert all(min(abs(float(v)), abs(float(v) - 1.0 / keep)) < 1e-6 for v in vals)
+            assert abs(float(s.mean()) - 1.0) < 0.05 and s.is_contiguous()
+    assert not torch.equal(sc[1][0], sc[1][1])                    # the two branches of a block draw independently
+    assert m.eval()._draw_drop_path(8, torch.device('cuda')) is None
