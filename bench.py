@@ -309,20 +309,30 @@ def main():
     if rank == 0:
         try:
             from devias_b200 import ops as _ops
-            Bm, Sm = 128, cfg['num_latents']
+            Bm, Sm = 256, cfg['num_latents']     # 1.23 GB of fp32 tokens: far beyond the 126 MB L2, every pass streams from HBM
             tok = torch.randn(Bm, 1568, 768, device=dev) * 1.5
             g_ = torch.randn(Bm, 4 * Sm, 768, device=dev) * 0.05
             G_ = g_.sum(-1).contiguous(); c0_ = torch.randn(Bm, 4 * Sm, device=dev)
-            for _ in range(3):
-                _ops.slot_stream_fwd(tok, g_, G_, c0_)
-            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            torch.cuda.synchronize(); s0.record()
-            for _ in range(10):
-                _ops.slot_stream_fwd(tok, g_, G_, c0_)
-            s1.record(); torch.cuda.synchronize()
-            t_ms = s0.elapsed_time(s1) / 10
+
+            def _time(fn, n=10):
+                for _ in range(3):
+                    fn()
+                s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize(); s0.record()
+                for _ in range(n):
+                    fn()
+                s1.record(); torch.cuda.synchronize()
+                return s0.elapsed_time(s1) / n
+            t_ms = _time(lambda: _ops.slot_stream_fwd(tok, g_, G_, c0_))
+            nbytes = Bm * 1568 * 768 * 4
             slot_micro = {'batch': Bm, 'slots': Sm, 'tokens_dtype': 'f32', 'us_per_pass': t_ms * 1e3,
-                          'gbs': Bm * 1568 * 768 * 4 / (t_ms * 1e-3) / 1e9}
+                          'gbs': nbytes / (t_ms * 1e-3) / 1e9}
+            if Sm in (2, 4):                      # streaming backward: reads the tokens, writes their gradient
+                U_, m_, A_, at_, mu_, r_ = _ops.slot_stream_fwd(tok, g_, G_, c0_)
+                dU_, dm_, dA_ = torch.randn_like(U_), torch.randn_like(m_), torch.randn_like(A_)
+                tb_ms = _time(lambda: _ops.slot_stream_bwd(tok, mu_, r_, g_, G_, at_, dU_, dm_, dA_))
+                slot_micro.update({'bwd_us_per_pass': tb_ms * 1e3, 'bwd_gbs': 2 * nbytes / (tb_ms * 1e-3) / 1e9})
+                del U_, m_, A_, at_, mu_, r_, dU_, dm_, dA_
             del tok, g_, G_, c0_
         except Exception as e:  # the micro-measure must never take the headline down
             slot_micro = {'error': repr(e)}
