@@ -48,3 +48,37 @@ def test_reference_arm_prints_the_contract_line():
     assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1 and d['cpu_baseline']['value'] == d['value']
     assert d['e2e'] == {'value': d['value'], 'unit': 'clips/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
     assert d['metric'].startswith('train clips/sec') and 'workload' in d['config']
+
+
+def test_agg_block_modules_match_the_oracle_on_cpu():
+    """PreNorm(Attention) / PreNorm(FeedForward) called directly (the non-streaming path) against the oracle's restatement of
+    agg_block/attention.py, plus cache_fn weight tying.  Plain torch: runs without a GPU."""
+    from oracle import devias_oracle as O
+    from devias_b200.agg_block.attention import Attention, FeedForward, PreNorm, cache_fn
+    sd = O.synth_state_dict(num_latents=2, agg_depth=2, agg_weights_tie=True, depth=0, seed=31)
+    p = 'agg_block.layers.0.'
+    attn = PreNorm(768, Attention(768, 768, heads=4, dim_head=512), context_dim=768)
+    ff = PreNorm(768, FeedForward(768, activation='gelu', mult=4))
+    attn.load_state_dict({k[len(p + '0.'):]: v for k, v in sd.items() if k.startswith(p + '0.')})
+    ff.load_state_dict({k[len(p + '2.'):]: v for k, v in sd.items() if k.startswith(p + '2.')})
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 2, 768, generator=g)
+    ctx = torch.randn(2, 40, 768, generator=g) * 1.5
+    with torch.no_grad():
+        out, sim = attn(x, context=ctx, k_pos=None, q_pos=None)
+        ref_out, ref_sim = O.slot_cross_attention(sd, p + '0.', x, ctx)
+        y = ff(x)
+        ref_y = O.slot_feed_forward(sd, p + '2.', x)
+    assert sim.shape == ref_sim.shape == (2 * 4, 2, 40)
+    assert torch.allclose(out, ref_out, rtol=1e-5, atol=1e-5) and torch.allclose(sim, ref_sim, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(y, ref_y, rtol=1e-5, atol=1e-5)
+    assert torch.allclose(sim.sum(1), torch.ones(8, 40), atol=1e-5)          # the slots compete for every token
+
+    make = cache_fn(lambda: FeedForward(8, activation='relu'))
+    a, b, c = make(_cache=True), make(_cache=True), make(_cache=False)
+    assert a is b and c is not a
+    try:
+        FeedForward(8)                                                        # default 'geglu' is rejected, as in the reference
+        raise AssertionError('geglu must raise')
+    except NotImplementedError:
+        pass
