@@ -12,7 +12,7 @@ legs may import this module. The product package ``devias_b200`` must never impo
 Parity pinning: the reference ships no tests / golden vectors.  The oracle is
 pinned against outputs of the *reference itself* executed in the build container
 (``oracle/make_golden.py`` -> ``tests/golden/*.npz``) and re-checked live against
-``/root/reference`` whenever that tree is present (``tests/test_oracle_vs_reference.py``).
+``/root/reference`` whenever that tree is present (``tests/test_oracle_golden.py::test_oracle_vs_live_reference``).
 
 Every function cites the reference file:line it restates (paths relative to the reference root).
 """
