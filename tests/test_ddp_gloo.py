@@ -87,3 +87,54 @@ def test_reducer_single_process_is_passthrough():
     for a, b in zip(m.parameters(), m2.parameters()):
         assert torch.allclose(a.grad, b.grad)
         assert a.grad.data_ptr() == red._views[a].data_ptr()
+
+
+def _worker_ranges(rank, world, port, q):
+    """the exchange pattern of engine.GraphedTrainStep: hooks off, the arena reduced as an upper and a lower range"""
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        m = _model()
+        red = GradReducer(m)
+        red.enabled = False
+        lower = list(m[0].parameters())                     # executed first in forward = last in backward
+        low_ids = {id(p) for p in lower}
+        upper = [p for p in red.params if id(p) not in low_ids]
+        lo_rng, up_rng = red.range_of(lower), red.range_of(upper)
+        total = sum((p.numel() + 7) // 8 * 8 for p in red.params)
+        assert sorted([lo_rng, up_rng]) == [(0, sorted([lo_rng, up_rng])[0][1]), (sorted([lo_rng, up_rng])[0][1], total)]
+        g = torch.Generator().manual_seed(1)
+        x = torch.randn(8, 37, generator=g); y = torch.randn(8, 19, generator=g)
+        xs, ys = x.chunk(world)[rank], y.chunk(world)[rank]
+        red.zero_grad()
+        ((m(xs) - ys) ** 2).mean().backward()
+        red.allreduce_range(*up_rng)
+        red.allreduce_range(*lo_rng)
+        try:
+            red.range_of([list(m.parameters())[0], list(m.parameters())[-1]])   # not contiguous in the arena
+            ok = False
+        except AssertionError:
+            ok = True
+        q.put((rank, [p.grad.clone().numpy() for p in m.parameters()], ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_range_exchange_world2_matches_single_process():
+    world, port = 2, _free_port()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_ranges, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    m = _model()
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(8, 37, generator=g); y = torch.randn(8, 19, generator=g)
+    ((m(x) - y) ** 2).mean().backward()
+    for a, b0, b1 in zip(m.parameters(), res[0][1], res[1][1]):
+        assert torch.allclose(a.grad, torch.from_numpy(b0), atol=1e-6) and (b0 == b1).all()
+    assert res[0][2] and res[1][2]
