@@ -34,6 +34,8 @@ _SIGS = {
     'devias_last_error': (c_char_p, []),
     'devias_launch_count': (c_int64, []),
     'devias_profile_begin': (c_int, []),
+    'devias_profile_begin_capture': (c_int, []),
+    'devias_profile_pause': (c_int, []),
     'devias_profile_end': (c_int, [c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
                                    ctypes.POINTER(c_int64)]),
     'devias_gemm_bf16': (c_int, [_P, c_int64, c_int, _P, c_int64, c_int, c_int, c_int, c_int, c_int, _P, c_int64, _P,
@@ -58,7 +60,9 @@ _SIGS = {
     'devias_debug_token_stream': (c_int, [_P, c_int, c_int, c_int, _P, _P]),
     'devias_skinny_nt': (c_int, [_P, _P, _P, c_int64, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     'devias_skinny_nn': (c_int, [_P, _P, _P, c_int64, _P, _P, c_int, c_int, c_int, c_int, _P]),
-    'devias_skinny_outer': (c_int, [_P, _P, _P, _P, _P, c_int64, _P, c_int64, c_int, c_int, c_int, c_int, _P]),
+    'devias_sumsq_f32': (c_int, [_P, c_int64, _P, _P]),
+    'devias_adamw_arena': (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, _P, _P, c_int64, c_int, _P]),
+    'devias_skinny_outer': (c_int, [_P, _P, _P, _P, _P, c_int64, _P, c_int64, c_int, c_int, c_int, c_int, c_int, _P]),
 }
 
 
@@ -91,8 +95,14 @@ def launch_count() -> int:
     return int(lib().devias_launch_count())
 
 
-def profile_begin():
-    check(lib().devias_profile_begin(), 'profile_begin')
+def profile_begin(capture_only=False):
+    """bracket every launch of the instrumented kernel families with CUDA events from now on; capture_only: only launches made
+    inside a stream capture (they become event-record nodes of the graph and are re-recorded by every replay)"""
+    check(lib().devias_profile_begin_capture() if capture_only else lib().devias_profile_begin(), 'profile_begin')
+
+
+def profile_pause():
+    check(lib().devias_profile_pause(), 'profile_pause')
 
 
 def profile_end(kind: int):

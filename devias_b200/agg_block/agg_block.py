@@ -79,7 +79,7 @@ class AggregationBlock(nn.Module):
     # ------------------------------------------------------------------------------------------
     def _layer_params(self, cross_attn):
         a = cross_attn.fn
-        return dict(norm_w=cross_attn.norm.weight, norm_b=cross_attn.norm.bias,
+        return dict(norm=cross_attn.norm, norm_w=cross_attn.norm.weight, norm_b=cross_attn.norm.bias,
                     ctx_w=cross_attn.norm_context.weight, ctx_b=cross_attn.norm_context.bias,
                     wq=a.to_q.weight, wk=a.to_k.weight, wv=a.to_v.weight,
                     wo=a.to_out[0].weight, bo=a.to_out[0].bias)
@@ -96,9 +96,10 @@ class AggregationBlock(nn.Module):
                                                     stream=slot_kernels.slot_stream, lin=slot_linear, sink=sink)
                 x = attn + x
                 net = cross_ff.fn.net                            # PreNorm(FeedForward): Linear, GELU, Dropout(0), Linear
-                h = slot_linear.linear(cross_ff.norm(x), net[0].weight, net[0].bias)
+                h = slot_linear.linear(slot_linear.layer_norm(x, cross_ff.norm), net[0].weight, net[0].bias)
                 x = slot_linear.linear(net[1](h), net[3].weight, net[3].bias) + x
-            return self.last_layer(x), sim
+            last = self.last_layer[0]
+            return (slot_linear.layer_norm(x, last) if isinstance(last, nn.LayerNorm) else last(x)), sim
 
     def forward(self, data):
         b, *axis = data.shape    # as in the reference (agg_block/agg_block.py:121-122) the channel dim counts as an axis

@@ -3,9 +3,11 @@
 parity), same return values.
 
 On the DEVIAS recipes `AggregationBlock.forward` never calls these modules' `forward`: it reads their parameters and runs the
-folded streaming path (devias_b200/slot_attention.py + csrc/slot_attn.cu).  The `forward` methods below serve the remaining
-configurations (post-norm, dropout, relu, direct use of a module) with plain tensor algebra written head-major
-(`[batch, head, row, dim]`) instead of the reference's `(b h)` merges.
+folded streaming path (devias_b200/slot_attention.py + csrc/slot_attn.cu).  Called directly with fp32 CUDA tensors the modules
+run on the same hand-written kernels: `PreNorm(Attention)` = the folded streaming layer, a bare `Attention` = the folded
+products against the un-normalised context (csrc/skinny.cu), `FeedForward` / `PreNorm(FeedForward)` = the slot-row products.
+Only the configurations no DEVIAS recipe uses (dropout > 0 in training, non-fp32 inputs, host tensors in unit tests of the
+module algebra) evaluate the plain tensor algebra below, written head-major (`[batch, head, row, dim]`).
 """
 import torch
 import torch.nn.functional as F
@@ -14,6 +16,11 @@ from torch import nn
 
 def exists(val):
     return val is not None
+
+
+def _kernel_ok(t):
+    """fp32 CUDA tensor: the hand-written kernels apply"""
+    return t is not None and torch.is_tensor(t) and t.is_cuda and t.dtype == torch.float32
 
 
 def default(val, d):
@@ -53,6 +60,22 @@ class PreNorm(nn.Module):
         self.norm_context = None if context_dim is None else nn.LayerNorm(context_dim)
 
     def forward(self, x, **kwargs):
+        ctx = kwargs.get('context')
+        if _kernel_ok(x):
+            from .. import slot_kernels, slot_linear
+            from .. import slot_attention as SA
+            if (isinstance(self.fn, Attention) and self.norm_context is not None and _kernel_ok(ctx) and ctx.shape[-1] == 768
+                    and kwargs.get('k_pos') is None and kwargs.get('q_pos') is None and self.fn._plain()):
+                a = self.fn               # the whole PreNorm(Attention) layer folded onto ONE pass over the context tokens
+                p = dict(norm=self.norm, norm_w=self.norm.weight, norm_b=self.norm.bias, ctx_w=self.norm_context.weight,
+                         ctx_b=self.norm_context.bias, wq=a.to_q.weight, wk=a.to_k.weight, wv=a.to_v.weight,
+                         wo=a.to_out[0].weight, bo=a.to_out[0].bias)
+                with torch.autocast('cuda', enabled=False):
+                    return SA.slot_attention_layer(x, ctx.reshape(ctx.shape[0], -1, ctx.shape[-1]), None, None, p,
+                                                   stream=slot_kernels.slot_stream, lin=slot_linear)
+            if self.norm_context is None and x.shape[-1] == 768:
+                with torch.autocast('cuda', enabled=False):
+                    return self.fn(slot_linear.layer_norm(x, self.norm), **kwargs)
         if self.norm_context is not None:
             kwargs = dict(kwargs, context=self.norm_context(kwargs['context']))
         return self.fn(self.norm(x), **kwargs)
@@ -94,6 +117,12 @@ class FeedForward(nn.Module):
                 nn.init.zeros_(layer.bias)
 
     def forward(self, x):
+        drop = self.net[2].p if isinstance(self.net[2], nn.Dropout) else 0.
+        if _kernel_ok(x) and x.shape[-1] % 4 == 0 and (drop == 0. or not self.training) and not isinstance(self.net[4], nn.Dropout):
+            from .. import slot_linear
+            with torch.autocast('cuda', enabled=False):
+                h = self.activation(slot_linear.linear(x, self.net[0].weight, self.net[0].bias))
+                return slot_linear.linear(h, self.net[3].weight, self.net[3].bias)
         return self.net(x)
 
 
@@ -127,8 +156,37 @@ class Attention(nn.Module):
         b, rows, _ = t.shape
         return t.view(b, rows, self.heads, -1).transpose(1, 2)
 
+    def _plain(self):
+        """no dropout is active: the fused paths apply"""
+        drop = self.to_out[1].p
+        return (drop == 0. or not self.training) and not isinstance(self.attn_matrix_dropout, nn.Dropout)
+
+    def _forward_kernels(self, x, context, k_pos, q_pos):
+        """The cross-attention folded onto the slot rows (same algebra as devias_b200/slot_attention.py without the context
+        LayerNorm): sim = (scale Wk_h^T q) . ctx_j and out = Wv_h (sum_j w_j ctx_j), every product on csrc/skinny.cu."""
+        from .. import slot_linear as L
+        b, n, _ = x.shape
+        h = self.heads
+        ctx = context.reshape(b, -1, context.shape[-1])
+        dh = self.to_q.weight.shape[0] // h
+        q = L.linear(x if q_pos is None else x + q_pos, self.to_q.weight).view(b, n, h, dh)
+        qt = L.fold_keys(q, self.to_k.weight) * self.query_sfmax_scale                     # [B, h, n, D]
+        keys_src = ctx if k_pos is None else ctx + k_pos
+        logits = L.bmm_nt(qt.reshape(b, h * n, -1), keys_src).view(b, h, n, -1)             # [B, h, n, m]
+        compete = F.softmax(logits, dim=-2)
+        m = compete.shape[-1]
+        sim_distill = compete.reshape(b * h, n, m)
+        weights = compete / (compete.sum(dim=-1, keepdim=True) + 1e-7)
+        cbar = L.bmm_nn(weights.reshape(b, h * n, m), ctx).view(b, h, n, -1)                # [B, h, n, D]
+        mixed = L.apply_values(cbar, self.to_v.weight)                                      # [B, n, h*dh]
+        return L.linear(mixed, self.to_out[0].weight, self.to_out[0].bias), sim_distill
+
     def forward(self, x, context=None, k_pos=None, q_pos=None):
         context = x if context is None else context
+        if _kernel_ok(x) and _kernel_ok(context) and x.dim() == 3 and self._plain() and x.shape[-1] % 4 == 0 \
+                and context.shape[-1] % 4 == 0:
+            with torch.autocast('cuda', enabled=False):
+                return self._forward_kernels(x, context, k_pos, q_pos)
         queries = self._heads_first(self.to_q(x if q_pos is None else x + q_pos))
         keys = self._heads_first(self.to_k(context if k_pos is None else context + k_pos))
         values = self._heads_first(self.to_v(context))

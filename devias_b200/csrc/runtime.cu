@@ -87,9 +87,25 @@ struct ProfRec { cudaEvent_t a, b; int kind; double work; };
 static std::vector<ProfRec> g_prof;
 static size_t g_prof_used = 0;
 static bool g_prof_on = false;
+static bool g_prof_capture_only = false;
+
+// Inside a stream capture the record becomes an EXTERNAL event-record node: every replay of the captured graph re-records the
+// event, and cudaEventElapsedTime reads the times of the last replay -- the kernels are timed inside the replayed step, under its
+// clocks, caches and back-to-back launch conditions.
+static void record(cudaEvent_t e, cudaStream_t s) {
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(s, &st) == cudaSuccess && st == cudaStreamCaptureStatusActive)
+    cudaEventRecordWithFlags(e, s, cudaEventRecordExternal);
+  else
+    cudaEventRecord(e, s);
+}
 
 int prof_begin(int kind, double work, cudaStream_t s) {
   if (!g_prof_on) return -1;
+  if (g_prof_capture_only) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &st) != cudaSuccess || st != cudaStreamCaptureStatusActive) return -1;
+  }
   if (g_prof_used == g_prof.size()) {
     ProfRec r{};
     if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return -1;
@@ -98,11 +114,11 @@ int prof_begin(int kind, double work, cudaStream_t s) {
   ProfRec& r = g_prof[g_prof_used];
   r.kind = kind;
   r.work = work;
-  cudaEventRecord(r.a, s);
+  record(r.a, s);
   return (int)g_prof_used++;
 }
 void prof_end(int id, cudaStream_t s) {
-  if (id >= 0) cudaEventRecord(g_prof[id].b, s);
+  if (id >= 0) record(g_prof[id].b, s);
 }
 
 }  // namespace dv
@@ -110,11 +126,22 @@ void prof_end(int id, cudaStream_t s) {
 extern "C" int devias_profile_begin(void) {
   dv::g_prof_used = 0;
   dv::g_prof_on = true;
+  dv::g_prof_capture_only = false;
+  return DEVIAS_OK;
+}
+extern "C" int devias_profile_begin_capture(void) {
+  dv::g_prof_used = 0;
+  dv::g_prof_on = true;
+  dv::g_prof_capture_only = true;
+  return DEVIAS_OK;
+}
+extern "C" int devias_profile_pause(void) {
+  dv::g_prof_on = false;
   return DEVIAS_OK;
 }
 extern "C" int devias_profile_end(int kind, double* total_ms, double* total_work, int64_t* launches) {
   using namespace dv;
-  g_prof_on = false;
+  g_prof_on = false;      // the records stay: a captured graph keeps re-recording them, so this may be called after every replay
   DV_CHECK_CUDA(cudaDeviceSynchronize());
   double ms = 0, work = 0;
   long long n = 0;

@@ -159,7 +159,7 @@ constexpr int kSkOutRows = 8;      // rows i of c per CTA
 
 __global__ void __launch_bounds__(256) skinny_outer_kernel(const float* __restrict__ a, RowMap am, const float* __restrict__ b, RowMap bm,
                                                            float* __restrict__ c, long long c_batch, float* __restrict__ colsum,
-                                                           long long colsum_batch, int M, int I, int J) {
+                                                           long long colsum_batch, int M, int I, int J, int accumulate) {
   __shared__ float4 as4[kSkOutRows * kSkMT / 4];                   // [8 rows i][16 m]
   const int tid = threadIdx.x, z = blockIdx.z;
   const int i0 = blockIdx.y * kSkOutRows;
@@ -207,9 +207,19 @@ __global__ void __launch_bounds__(256) skinny_outer_kernel(const float* __restri
     float* cz = c + (long long)z * c_batch;
 #pragma unroll
     for (int i = 0; i < kSkOutRows; ++i)
-      if (i0 + i < I) reinterpret_cast<float4*>(cz + (long long)(i0 + i) * J)[j4] = acc[i];
+      if (i0 + i < I) {
+        float4* dst = reinterpret_cast<float4*>(cz + (long long)(i0 + i) * J) + j4;
+        if (accumulate) {       // gradient arena mode: every (i, j) is owned by exactly one thread, plain read-modify-write
+          const float4 o = *dst;
+          acc[i].x += o.x; acc[i].y += o.y; acc[i].z += o.z; acc[i].w += o.w;
+        }
+        *dst = acc[i];
+      }
   }
-  if (colsum != nullptr && blockIdx.x == 0 && tid < kSkOutRows && i0 + tid < I) colsum[(long long)z * colsum_batch + i0 + tid] = cs;
+  if (colsum != nullptr && blockIdx.x == 0 && tid < kSkOutRows && i0 + tid < I) {
+    float* d = colsum + (long long)z * colsum_batch + i0 + tid;
+    *d = accumulate ? *d + cs : cs;
+  }
 }
 
 static RowMap make_map(const int64_t* m) {
@@ -260,7 +270,7 @@ extern "C" int devias_skinny_nn(const float* x, const int64_t* x_map, const floa
 
 extern "C" int devias_skinny_outer(const float* a, const int64_t* a_map, const float* b, const int64_t* b_map, float* c,
                                    int64_t c_batch, float* colsum, int64_t colsum_batch, int M, int I, int J, int batch,
-                                   void* stream) {
+                                   int accumulate, void* stream) {
   DV_REQUIRE(a && b && c, "null pointer");
   DV_REQUIRE(M > 0 && I > 0 && J > 0 && batch > 0 && J % 4 == 0, "skinny_outer: J must be a multiple of 4");
   DV_REQUIRE(a_map && a_map[1] > 0 && map_ok(b_map) && c_batch % 4 == 0, "skinny_outer: row maps must keep 16-byte alignment");
@@ -269,7 +279,7 @@ extern "C" int devias_skinny_outer(const float* a, const int64_t* a_map, const f
   const int threads = j4 >= 256 ? 256 : (j4 + 31) / 32 * 32;
   const dim3 grid((j4 + threads - 1) / threads, (I + kSkOutRows - 1) / kSkOutRows, batch);
   skinny_outer_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(a, make_map(a_map), b, make_map(b_map), c, c_batch, colsum,
-                                                                 colsum_batch, M, I, J);
+                                                                 colsum_batch, M, I, J, accumulate);
   DV_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return DEVIAS_OK;

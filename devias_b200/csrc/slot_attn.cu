@@ -604,13 +604,18 @@ struct SlotBwdParams {
   const float* dattn;                     // [B, HS, N] or null
   float* dt; int accumulate;              // [B, N, 768]
   float* dg; float* dG; float* dc0;       // (+=)
+  int hs_total, hs_off;                   // rows per clip in g / G / a / dU / ... and the first row this launch handles
 };
 
-template <int HS>
+// HEADS heads x S = HS / HEADS slots per launch; the (head, slot) rows handled are [hs_off, hs_off + HS) of hs_total per clip.
+// Every term of dt / dmu / dr is a sum over (head, slot), so S = 8 (32 rows: g and dU of all heads do not fit in shared memory)
+// runs as two launches over two heads each, the second accumulating onto the first.
+template <int HS, int HEADS>
 __global__ void __launch_bounds__(kSlotThreads, 1)
 slot_stream_bwd_kernel(const __grid_constant__ CUtensorMap tmTok, const SlotBwdParams p) {
   using Cfg = SlotBwdCfg<HS>;
-  constexpr int S = HS / 4;
+  constexpr int S = HS / HEADS;
+  const long long row0 = (long long)blockIdx.y * p.hs_total + p.hs_off;      // first (head, slot) row of this clip / launch
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* g_s = reinterpret_cast<float*>(smem + Cfg::OFF_G);
@@ -632,8 +637,8 @@ slot_stream_bwd_kernel(const __grid_constant__ CUtensorMap tmTok, const SlotBwdP
     fence_barrier_init();
   }
   {
-    const float4* sg = reinterpret_cast<const float4*>(p.g + (long long)b * HS * kSD);
-    const float4* sd = reinterpret_cast<const float4*>(p.dU + (long long)b * HS * kSD);
+    const float4* sg = reinterpret_cast<const float4*>(p.g + row0 * kSD);
+    const float4* sd = reinterpret_cast<const float4*>(p.dU + row0 * kSD);
     for (int i = tid; i < HS * kSD / 4; i += kSlotThreads) {
       reinterpret_cast<float4*>(g_s)[i] = __ldg(sg + i);
       reinterpret_cast<float4*>(du_s)[i] = __ldg(sd + i);
@@ -664,9 +669,9 @@ slot_stream_bwd_kernel(const __grid_constant__ CUtensorMap tmTok, const SlotBwdP
       dgacc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
-  const float* Gs = p.G + b * HS;
-  const float* dms = p.dm + b * HS;
-  const float* dAs = p.dA + b * HS;
+  const float* Gs = p.G + row0;
+  const float* dms = p.dm + row0;
+  const float* dAs = p.dA + row0;
 
   const int tok_l = lane & 15, half = lane >> 4;
   const int slice = warp * 2 + half;
@@ -724,17 +729,17 @@ slot_stream_bwd_kernel(const __grid_constant__ CUtensorMap tmTok, const SlotBwdP
       float dr = 0.f, dmu = 0.f;
       float* cf = coef + lane * Cfg::COEF_STRIDE;
 #pragma unroll
-      for (int h = 0; h < 4; ++h) {
+      for (int h = 0; h < HEADS; ++h) {
         float av[S], da[S];
         float dot = 0.f;
 #pragma unroll
         for (int s = 0; s < S; ++s) {
           const int i = h * S + s;
-          av[s] = valid ? __ldg(p.a + ((long long)b * HS + i) * p.N + tok) : 0.f;
+          av[s] = valid ? __ldg(p.a + (row0 + i) * p.N + tok) : 0.f;
           e[i] -= mu * __ldg(Gs + i);
           f[i] += mu * __ldg(dms + i);
           da[s] = fmaf(r, f[i], __ldg(dAs + i));
-          if (p.dattn != nullptr && valid) da[s] += __ldg(p.dattn + ((long long)b * HS + i) * p.N + tok);
+          if (p.dattn != nullptr && valid) da[s] += __ldg(p.dattn + (row0 + i) * p.N + tok);
           dot = fmaf(av[s], da[s], dot);
         }
 #pragma unroll
@@ -793,7 +798,7 @@ slot_stream_bwd_kernel(const __grid_constant__ CUtensorMap tmTok, const SlotBwdP
     __syncthreads();
   }
   if (tid < kSD / 4) {
-    float* dst = p.dg + (long long)b * HS * kSD + tid * 4;
+    float* dst = p.dg + row0 * kSD + tid * 4;
 #pragma unroll
     for (int i = 0; i < HS; ++i) red_add_v4_f32(dst + i * kSD, dgacc[i].x, dgacc[i].y, dgacc[i].z, dgacc[i].w);
   }
@@ -801,8 +806,8 @@ slot_stream_bwd_kernel(const __grid_constant__ CUtensorMap tmTok, const SlotBwdP
     float a = 0.f, c = 0.f;
 #pragma unroll
     for (int j = 0; j < kST; ++j) { a += accG[j * HS + tid]; c += accC[j * HS + tid]; }
-    atomicAdd(p.dG + b * HS + tid, a);
-    atomicAdd(p.dc0 + b * HS + tid, c);
+    atomicAdd(p.dG + row0 + tid, a);
+    atomicAdd(p.dc0 + row0 + tid, c);
   }
 }
 
@@ -1101,11 +1106,11 @@ static int launch_slot_bwd2(const CUtensorMap& tm, const SlotBwdParams& p, cudaS
   return DEVIAS_OK;
 }
 
-template <int HS>
+template <int HS, int HEADS>
 static int launch_slot_bwd(const CUtensorMap& tm, const SlotBwdParams& p, int splits, cudaStream_t s) {
   using Cfg = SlotBwdCfg<HS>;
   static_assert(Cfg::BYTES <= 227 * 1024, "slot backward does not fit in shared memory");
-  auto kern = slot_stream_bwd_kernel<HS>;
+  auto kern = slot_stream_bwd_kernel<HS, HEADS>;
   static bool attr_done = false;
   if (!attr_done) {
     DV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::BYTES));
@@ -1240,11 +1245,7 @@ extern "C" int devias_slot_stream_bwd(const float* tokens, const float* mu, cons
   using namespace dv;
   DV_REQUIRE(tokens && mu && rstd && g && G && attn && dU && dm && dA && dtokens && dg && dG && dc0, "null pointer");
   DV_REQUIRE(dim == kSD, "token dim must be 768");
-  if (num_slots != 2 && num_slots != 4) {
-    set_last_error("num_slots", "the streaming backward is instantiated for 2 and 4 slots (g and dU must fit in shared memory)",
-                   __FILE__, __LINE__);
-    return DEVIAS_ERR_UNSUPPORTED;
-  }
+  DV_REQUIRE(num_slots == 2 || num_slots == 4 || num_slots == 8, "num_slots must be 2, 4 or 8");
   DV_REQUIRE(batch > 0 && n_tokens > 0, "empty problem");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   CUtensorMap tm;
@@ -1257,9 +1258,15 @@ extern "C" int devias_slot_stream_bwd(const float* tokens, const float* mu, cons
   const int per = (tiles + splits - 1) / splits;
   splits = (tiles + per - 1) / per;
   SlotBwdParams p{batch, n_tokens, num_slots, per, tiles, mu, rstd, g, G, attn, dU, dm, dA, dattn, dtokens, accumulate_dtokens,
-                  dg, dG, dc0};
+                  dg, dG, dc0, 4 * num_slots, 0};
   if (num_slots == 2) return launch_slot_bwd2(tm, p, s);
-  return launch_slot_bwd<16>(tm, p, splits, s);
+  if (num_slots == 4) return launch_slot_bwd<16, 4>(tm, p, splits, s);
+  // S = 8: heads {0, 1} then heads {2, 3}; the second pass adds its share of dt onto the first
+  rc = launch_slot_bwd<16, 2>(tm, p, splits, s);
+  if (rc) return rc;
+  p.hs_off = 16;
+  p.accumulate = 1;
+  return launch_slot_bwd<16, 2>(tm, p, splits, s);
 }
 
 extern "C" int devias_debug_token_stream(const float* tokens, int batch, int n_tokens, int stages, float* scratch, void* stream) {

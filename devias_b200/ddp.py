@@ -16,14 +16,16 @@ import torch.distributed as dist
 
 class GradReducer:
     def __init__(self, module: torch.nn.Module, bucket_mb: float = 48.0, process_group=None, first_bucket_mb: float = 8.0):
+        from .arena import ParamArena
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
-        params = [p for p in module.parameters() if p.requires_grad]
-        params = params[::-1]                                   # ~ reverse execution order: head/agg first, patch_embed last
+        # parameters AND gradients live in the module's flat arena (reverse execution order: head / agg first, patch_embed last)
+        self.param_arena = pa = ParamArena.of(module)
+        params = pa.params
         self.params = params
         self.buckets: List[torch.Tensor] = []
         self.bucket_of = {}
-        self._views = {}
+        self._views = {p: pa.grad_view(p) for p in params}
         cap = int(first_bucket_mb * (1 << 20) // 4)
         cur, cur_n = [], 0
         groups = []
@@ -37,26 +39,19 @@ class GradReducer:
             cur_n += n
         if cur:
             groups.append(cur)
-        sizes = [sum((p.numel() + 7) // 8 * 8 for p in g) for g in groups]
         # all buckets are slices of ONE arena, so the un-overlapped path can exchange everything with a single collective
-        self.arena = torch.zeros(sum(sizes), device=params[0].device, dtype=torch.float32)
+        self.arena = pa.grad
         self._avg = dist.is_initialized() and dist.get_backend(process_group) == 'nccl'   # NCCL averages natively
-        start = 0
         for bi, g in enumerate(groups):
-            total = sizes[bi]
-            flat = self.arena[start:start + total]
-            start += total
-            off = 0
+            lo, hi = pa.range_of(g)
             for p in g:
-                self._views[p] = flat[off:off + p.numel()].view(p.shape)
                 self.bucket_of[p] = bi
-                off += (p.numel() + 7) // 8 * 8
-            self.buckets.append(flat)
+            self.buckets.append(self.arena[lo:hi])
         self.sizes = [len(g) for g in groups]
         self._pending = [0] * len(groups)
         self._works: List[Optional[object]] = []
         self._launched = [False] * len(groups)
-        self.enabled = True                                      # set False on gradient-accumulation micro-steps
+        self.enabled = True                                      # False on gradient-accumulation micro-steps (begin_backward)
         self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in params]
         self.zero_grad()
 
@@ -71,13 +66,28 @@ class GradReducer:
         self._launched = [False] * len(self.buckets)
         self._works = []
 
+    def reset_step(self):
+        """start of a new step when somebody else (the arena optimizer pass) already zero-filled the gradients"""
+        self._pending = list(self.sizes)
+        self._launched = [False] * len(self.buckets)
+        self._works = []
+
+    def begin_backward(self, exchange=True):
+        """call before every backward of a step.  exchange=False marks a gradient-accumulation micro-step: its gradients are
+        summed into the arena but not counted in, so no bucket is all-reduced before the last micro-step's backward has added
+        its share (a bucket exchanged early would be exchanged without the later micro-steps' gradients)."""
+        self.enabled = bool(exchange)
+        if exchange:
+            assert not any(self._launched), 'a bucket was already exchanged in this step (finish() / zero_grad() missing?)'
+            self._pending = list(self.sizes)
+
     def _on_grad(self, p):
-        if not self.enabled:
-            return
-        b = self.bucket_of[p]
         if p.grad.data_ptr() != self._views[p].data_ptr():       # someone replaced .grad (e.g. set_to_none): re-home it
             self._views[p].copy_(p.grad)
             p.grad = self._views[p]
+        if not self.enabled:
+            return
+        b = self.bucket_of[p]
         self._pending[b] -= 1
         if self._pending[b] == 0 and not self._launched[b]:
             self._launch(b)
@@ -91,6 +101,9 @@ class GradReducer:
     def finish(self):
         """call after backward, before the optimizer step"""
         if not self.enabled:
+            if self.world > 1:
+                raise RuntimeError('GradReducer.finish() on a reducer whose exchange is switched off: the ranks would step on '
+                                   'their local gradients (call begin_backward(exchange=True) before the last backward)')
             return
         for b in range(len(self.buckets)):
             if not self._launched[b]:                            # parameters that received no gradient this step
@@ -115,17 +128,7 @@ class GradReducer:
     def range_of(self, params):
         """[lo, hi) slice of the arena holding exactly the gradients of `params` (which must be a prefix or a suffix of
         the reducer's reverse-execution parameter order)"""
-        ids = {id(p) for p in params}
-        lo, hi, off = None, None, 0
-        for p in self.params:
-            n = (p.numel() + 7) // 8 * 8
-            if id(p) in ids:
-                lo = off if lo is None else lo
-                hi = off + n
-            off += n
-        inside = sum((p.numel() + 7) // 8 * 8 for p in self.params if id(p) in ids)
-        assert lo is not None and hi - lo == inside, 'parameters are not contiguous in the gradient arena'
-        return lo, hi
+        return self.param_arena.range_of(params)
 
     def allreduce_range(self, lo, hi, async_op=False):
         if self.world <= 1:

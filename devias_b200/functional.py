@@ -6,6 +6,7 @@ residual stream is fp32, GEMM operands are bf16 (fp32 accumulation in tensor mem
 """
 from __future__ import annotations
 
+import contextlib
 from typing import Optional
 
 import torch
@@ -13,38 +14,77 @@ import torch
 from . import ops
 
 # --------------------------------------------------------------------------------------------
+# direct gradient accumulation: inside `direct_grads()` the backward Functions of this package reduce-add every parameter
+# gradient straight into the flat gradient arena (`param._grad_sink`, devias_b200/arena.py) and hand autograd None for it, so
+# no per-parameter accumulation kernels, zero fills or temporaries exist.  Used by the captured training step (engine.py),
+# where python gradient hooks do not run anyway; eager DDP (hook-driven buckets) keeps the autograd route.
+_direct = False
+
+
+@contextlib.contextmanager
+def direct_grads(enable=True):
+    global _direct
+    prev, _direct = _direct, bool(enable)
+    try:
+        yield
+    finally:
+        _direct = prev
+
+
+def grad_sinks(*params):
+    """arena gradient views of `params` if direct accumulation is on and ALL of them live in an arena, else None"""
+    if not _direct:
+        return None
+    out = [getattr(p, '_grad_sink', None) if getattr(p, 'requires_grad', False) else None for p in params]
+    return out if all(s is not None for s in out) else None
+
+# --------------------------------------------------------------------------------------------
 # side channel: the LayerNorm-backward kernel that produces a residual-stream gradient (fp32) also
 # emits its bf16 copy (the operand of the next dgrad/wgrad GEMMs).  autograd only carries the fp32
-# tensor between Functions; the copy travels here, keyed by (data_ptr, version).
+# tensor between Functions; the copy travels here, tied to the IDENTITY of the producing tensor object (a weak reference --
+# a recycled address or a summed / replaced gradient can never match) and its version at the time of the stash.
 # The copy may already carry the per-sample drop-path factor of the branch that consumes it next (`scale`, matched by
 # identity) and comes with its column sums (= the bias gradient of that branch's last linear layer).
-_bf16_of = {}
+import weakref
+
+_stash = None      # (weakref to dx, version, dxb, scale, colsum)
 
 
 def _stash_bf16(dx: torch.Tensor, dxb: torch.Tensor, scale=None, colsum=None):
-    _bf16_of.clear()
-    _bf16_of[(dx.data_ptr(), dx._version)] = (dxb, scale, colsum)
+    global _stash
+    _stash = (weakref.ref(dx), dx._version, dxb, scale, colsum)
+
+
+def _match(dx: torch.Tensor):
+    t = _stash
+    if t is not None and t[0]() is dx and t[1] == dx._version and t[2].shape == dx.shape:
+        return t
+    return None
 
 
 def _is_ours(dx: torch.Tensor) -> bool:
-    """True when `dx` was produced (and stashed) by one of our own backward kernels, i.e. nobody else can alias it."""
-    return (dx.data_ptr(), dx._version) in _bf16_of
+    """True when `dx` is the very tensor one of our own backward kernels produced (and stashed): nobody else can alias it."""
+    return _match(dx) is not None
 
 
 def _take_bf16(dx: torch.Tensor) -> torch.Tensor:
     """unscaled bf16 copy of a residual-stream gradient"""
-    t = _bf16_of.pop((dx.data_ptr(), dx._version), None)
-    if t is not None and t[1] is None and t[0].shape == dx.shape:
-        return t[0]
+    global _stash
+    t = _match(dx)
+    _stash = None
+    if t is not None and t[3] is None:
+        return t[2]
     return ops.cast_bf16(dx.contiguous())
 
 
 def _take_scaled(dx: torch.Tensor, scale, rows_per_scale: int):
     """(bf16(dx * scale per sample), column sums of it | None): straight from the producing LayerNorm backward when it was told
     this consumer's scale, otherwise by the stand-alone cast kernel."""
-    t = _bf16_of.pop((dx.data_ptr(), dx._version), None)
-    if t is not None and t[1] is scale and t[0].shape == dx.shape:
-        return t[0], t[2]
+    global _stash
+    t = _match(dx)
+    _stash = None
+    if t is not None and t[3] is scale:
+        return t[2], t[4]
     if scale is None:
         return ops.cast_bf16(dx.contiguous()), None
     return ops.scale_rows_cast(dx, scale, rows_per_scale), None
@@ -82,6 +122,7 @@ class PatchEmbedFn(torch.autograd.Function):
         x0 = ops.gemm(patches, w16.view(D, -1), ops.EPI_RESID_F32, bias=bias, aux=pos_table, aux_row_mod=N)
         ctx.save_for_backward(patches)
         ctx.wshape = weight.shape
+        ctx.sinks = grad_sinks(weight, bias)
         return x0.view(B, N, D)
 
     @staticmethod
@@ -89,10 +130,16 @@ class PatchEmbedFn(torch.autograd.Function):
         (patches,) = ctx.saved_tensors
         D = ctx.wshape[0]
         dyb = _take_bf16(dx0).view(-1, D)
-        dw, db = _flat_zeros([torch.empty(D, patches.shape[1], device='meta'), torch.empty(D, device='meta')], dx0.device)
+        direct = ctx.sinks is not None
+        if direct:
+            dw, db = ctx.sinks[0].view(D, -1), ctx.sinks[1]
+        else:
+            dw, db = _flat_zeros([torch.empty(D, patches.shape[1], device='meta'), torch.empty(D, device='meta')], dx0.device)
         ops.gemm(dyb, patches, ops.EPI_ATOMIC_F32, a_mn=True, b_mn=True, out=dw,
                  split_k=_wgrad_split(D, patches.shape[1], patches.shape[0]))
         ops.colsum_bf16(dyb, db)
+        if direct:
+            return None, None, None, None, None
         return None, dw.view(ctx.wshape), db, None, None
 
 
@@ -106,16 +153,24 @@ class LayerNormFn(torch.autograd.Function):
         x = x.contiguous()
         y, mean, rstd = ops.layernorm_fwd(x, weight, bias, eps, out_dtype)
         ctx.save_for_backward(x, mean, rstd, weight, below_scale)
+        ctx.sinks = grad_sinks(weight, bias)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, mean, rstd, weight, below = ctx.saved_tensors
-        dg, db, cs = _flat_zeros([weight, weight, weight], x.device)
+        direct = ctx.sinks is not None
+        if direct:
+            dg, db = ctx.sinks
+            (cs,) = _flat_zeros([weight], x.device)
+        else:
+            dg, db, cs = _flat_zeros([weight, weight, weight], x.device)
         rows_per = (x.numel() // x.shape[-1]) // below.numel() if below is not None else 1
         dx, dxb = ops.layernorm_bwd(dy.contiguous(), x, mean, rstd, weight, dgamma=dg, dbeta=db, dx_colsum=cs, row_scale=below,
                                     rows_per_scale=rows_per)
         _stash_bf16(dx, dxb, below, cs)
+        if direct:
+            return dx, None, None, None, None, None
         return dx, dg, db, None, None, None
 
 
@@ -160,6 +215,7 @@ class EncoderBlockFn(torch.autograd.Function):
             ctx.attn_state = attn_state
             ctx.dims = (B, N, D)
             ctx.shapes = [t.shape for t in (n1w, n1b, qkv_w, q_bias, v_bias, proj_w, proj_b, n2w, n2b, fc1_w, fc1_b, fc2_w, fc2_b)]
+            ctx.sinks = grad_sinks(n1w, n1b, qkv_w, q_bias, v_bias, proj_w, proj_b, n2w, n2b, fc1_w, fc1_b, fc2_w, fc2_b)
         return x2.view(B, N, D)
 
     @staticmethod
@@ -171,16 +227,23 @@ class EncoderBlockFn(torch.autograd.Function):
         dev = dx2.device
         dx2 = dx2.contiguous()
         ours = _is_ours(dx2)   # our own LN-backward output may be updated in place along the residual chain
-        metas = [torch.empty(s, device='meta') for s in ctx.shapes] + [torch.empty(D, device='meta')]
-        (dn1w, dn1b, dqkv_w, dq_bias, dv_bias, dproj_w, dproj_b, dn2w, dn2b, dfc1_w, dfc1_b, dfc2_w, dfc2_b, below_cs) = \
-            _flat_zeros(metas, dev)
+        direct = ctx.sinks is not None
+        if direct:       # parameter gradients accumulate straight into the gradient arena
+            (dn1w, dn1b, dqkv_w, dq_bias, dv_bias, dproj_w, dproj_b, dn2w, dn2b, dfc1_w, dfc1_b, dfc2_w, dfc2_b) = ctx.sinks
+            (below_cs,) = _flat_zeros([torch.empty(D, device='meta')], dev)
+        else:
+            metas = [torch.empty(s, device='meta') for s in ctx.shapes] + [torch.empty(D, device='meta')]
+            (dn1w, dn1b, dqkv_w, dq_bias, dv_bias, dproj_w, dproj_b, dn2w, dn2b, dfc1_w, dfc1_b, dfc2_w, dfc2_b, below_cs) = \
+                _flat_zeros(metas, dev)
         Hd = fc116.shape[0]
         # ---- MLP branch: x2 = x1 + s2 * (gelu(x1n W1^T + b1) W2^T + b2)
         dyb, cs = _take_scaled(dx2, s2, N)
         dyb = dyb.view(M, D)
         dh = ops.gemm(dyb, fc216, ops.EPI_DGELU_BF16, b_mn=True, aux=h_pre)            # [M, Hd]
         ops.gemm(dyb, h_act, ops.EPI_ATOMIC_F32, a_mn=True, b_mn=True, out=dfc2_w, split_k=_wgrad_split(D, Hd, M))
-        if cs is not None:
+        if cs is not None and direct:
+            dfc2_b.add_(cs.view(dfc2_b.shape))
+        elif cs is not None:
             dfc2_b = cs.view(dfc2_b.shape)           # column sums came with the operand from the producing LayerNorm backward
         else:
             ops.colsum_bf16(dyb, dfc2_b)
@@ -206,5 +269,7 @@ class EncoderBlockFn(torch.autograd.Function):
                                     dx_colsum=below_cs, inplace=True, row_scale=below, rows_per_scale=N)
         dx = dx.view(B, N, D)
         _stash_bf16(dx, dxb.view(B, N, D), below, below_cs)
+        if direct:
+            return (dx,) + (None,) * 19
         return (dx, dn1w, dn1b, dqkv_w, dq_bias, dv_bias, dproj_w, dproj_b, dn2w, dn2b, dfc1_w, dfc1_b,
                 dfc2_w, dfc2_b, None, None, None, None, None, None)

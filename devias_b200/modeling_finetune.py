@@ -108,6 +108,11 @@ class VisionTransformer(nn.Module):
                     self._zero_pos = torch.zeros(n_patch, self.embed_dim, device=dev)
                 x = self.patch_embed(x, pos_table=self._zero_pos, w16=pe16)
                 x = torch.cat((self.cls_token.expand(x.size(0), -1, -1), x), dim=1) + self._pos_dev
+            elif isinstance(self.pos_embed, nn.Parameter):
+                # learnable table (model/modeling_finetune.py:221-222): added differentiably so that it receives its gradient
+                if self._zero_pos is None or self._zero_pos.device != dev:
+                    self._zero_pos = torch.zeros(n_patch, self.embed_dim, device=dev)
+                x = self.patch_embed(x, pos_table=self._zero_pos, w16=pe16) + self.pos_embed
             else:
                 x = self.patch_embed(x, pos_table=self._pos_dev[0].contiguous(), w16=pe16)
             x = x.contiguous()

@@ -348,9 +348,18 @@ class VisionTransformer(nn.Module):
         """call after modifying weights through `.data` (which does not bump tensor versions)"""
         if self._arena is not None:
             self._arena.stamp = None
+        if self.__dict__.get('_param_arena') is not None:
+            self._param_arena.invalidate16()
 
     def _weights16(self):
         gemm_params = [self.patch_embed.proj.weight] + [w for b in self.blocks for w in b.gemm_weights()]
+        pa = self.__dict__.get('_param_arena')
+        if pa is not None and pa.valid() and all(pa.contains(p) for p in gemm_params):
+            # training arena (devias_b200/arena.py): the optimizer pass keeps the bf16 shadow fresh; re-cast only when someone
+            # modified parameters through torch (load_state_dict, a torch optimizer)
+            pa.refresh16()
+            v = [pa.view16(p) for p in gemm_params]
+            return v[0], [tuple(v[1 + 4 * i: 5 + 4 * i]) for i in range(len(self.blocks))]
         if self._arena is None or not self._arena.valid() or self._arena.params[0].device != gemm_params[0].device:
             self._arena = _WeightArena(gemm_params)
         self._arena.refresh(force=self.training and torch.is_grad_enabled())

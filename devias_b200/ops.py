@@ -191,16 +191,23 @@ def skinny_nn(x: torch.Tensor, w: torch.Tensor, y: torch.Tensor):
     return y
 
 
-def skinny_outer(a: torch.Tensor, b: torch.Tensor, want_colsum=False):
-    """c[z] = a[z].T @ b[z]  ([Z, I, J]);  optionally colsum[z, i] = sum_m a[z, m, i]"""
+def skinny_outer(a: torch.Tensor, b: torch.Tensor, want_colsum=False, into=None, colsum_into=None):
+    """c[z] = a[z].T @ b[z]  ([Z, I, J]);  optionally colsum[z, i] = sum_m a[z, m, i].
+    into / colsum_into: contiguous [Z, I, J] / [Z, I] buffers that are ACCUMULATED into (+=) instead of allocating results."""
     _need_cuda(a)
     Z, I, J = a.shape[0], a.shape[-1], b.shape[-1]
     M = a.numel() // (Z * I)
     assert a.dtype == b.dtype == torch.float32 and b.shape[0] == Z and b.numel() == Z * M * J
-    c = torch.empty(Z, I, J, device=a.device, dtype=torch.float32)
-    cs = torch.empty(Z, I, device=a.device, dtype=torch.float32) if want_colsum else None
+    acc = into is not None
+    if acc:
+        assert into.is_contiguous() and into.numel() == Z * I * J and into.dtype == torch.float32
+        c, cs = into, colsum_into
+        assert cs is None or (cs.is_contiguous() and cs.numel() == Z * I)
+    else:
+        c = torch.empty(Z, I, J, device=a.device, dtype=torch.float32)
+        cs = torch.empty(Z, I, device=a.device, dtype=torch.float32) if want_colsum else None
     rc = _lib.lib().devias_skinny_outer(a.data_ptr(), rowmap(a), b.data_ptr(), rowmap(b), c.data_ptr(), I * J, _ptr(cs), I, M, I, J, Z,
-                                        _stream())
+                                        int(acc), _stream())
     _lib.check(rc, 'skinny_outer')
     return c, cs
 

@@ -53,7 +53,10 @@ def slot_attention_layer(x, tokens, mu, r, p, stream=slot_stream_torch, lin=None
     H = HEADS
     dh = p['wq'].shape[0] // H
     linear = F.linear if lin is None else lin.linear
-    xn = F.layer_norm(x, (D,), p['norm_w'], p['norm_b'], 1e-5)
+    if lin is None:
+        xn = F.layer_norm(x, (D,), p['norm_w'], p['norm_b'], 1e-5)
+    else:
+        xn = lin.layer_norm(x, p['norm'])
     q = linear(xn, p['wq']).view(B, S, H, dh)
     if lin is None:
         qt = torch.einsum('bshd,hdc->bhsc', q, p['wk'].view(H, dh, D)) * (dh ** -0.5)     # [B,H,S,D]

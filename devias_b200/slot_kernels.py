@@ -4,7 +4,6 @@ layer's backward kernel accumulates into one shared buffer and only the last one
 import torch
 
 from . import ops
-from . import slot_attention as SA
 
 
 def token_stats(tokens: torch.Tensor, eps: float = 1e-5):
@@ -28,7 +27,6 @@ class SlotStreamFn(torch.autograd.Function):
         ctx.save_for_backward(tokens, g, G, attn, mu, rstd)
         ctx.c0 = c0
         ctx.sink = sink
-        ctx.cuda_bwd = g.shape[1] in (8, 16)
         if sink is not None:
             sink.pending += 1
         ctx.mark_non_differentiable(mu, rstd)
@@ -41,16 +39,6 @@ class SlotStreamFn(torch.autograd.Function):
         dU = zeros(g) if dU is None else dU
         dm = zeros(G) if dm is None else dm
         dA = zeros(G) if dA is None else dA
-        if not ctx.cuda_bwd:
-            # S = 8 (micro-benchmark configuration only): g and dU do not fit in shared memory next to the token ring;
-            # the same folded expressions are differentiated by autograd on the GPU.
-            with torch.enable_grad():
-                leaves = [t.detach().requires_grad_(True) for t in (tokens, g, G, ctx.c0)]
-                mu2, r2 = SA.token_stats(leaves[0])
-                outs = SA.slot_stream_torch(leaves[0], mu2, r2, leaves[1], leaves[2], leaves[3])
-                go = [dU, dm, dA, zeros(attn) if dattn is None else dattn]
-                grads = torch.autograd.grad(outs, leaves, go, allow_unused=True)
-            return grads[0], grads[1], grads[2], grads[3], None
         sink = ctx.sink
         need_dt = ctx.needs_input_grad[0]
         if sink is not None and need_dt:

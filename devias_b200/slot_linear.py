@@ -1,14 +1,13 @@
 """Slot-side products on the CUDA `skinny_*` kernels (csrc/skinny.cu): every projection the aggregation block and the heads
 apply to the B*S slot rows -- agg_block/attention.py:120-141 (to_q, to_out, and to_k / to_v folded onto the slots as in
 devias_b200/slot_attention.py), :81-82 (FeedForward), model/modeling_slot.py:390-410 (head, mask predictor) -- with their
-gradients.  fp32 throughout.  Above MAX_ROWS rows (large evaluation batches) the products are no longer weight-read bound
-and go to the library GEMM instead."""
+gradients.  fp32 throughout, any number of rows (the kernels tile over the rows; weights are re-read from L2 per 16-row
+tile).  Inside `functional.direct_grads()` weight / bias gradients are accumulated straight into the gradient arena (which is
+also how the contributions of weight-tied layers are summed without extra launches)."""
 import torch
-import torch.nn.functional as F
 
 from . import ops
-
-MAX_ROWS = 32
+from .functional import grad_sinks
 
 
 class _LinearFn(torch.autograd.Function):
@@ -25,6 +24,7 @@ class _LinearFn(torch.autograd.Function):
         ctx.save_for_backward(x2, w)
         ctx.has_bias = b is not None
         ctx.xshape = x.shape
+        ctx.sinks = grad_sinks(w, b) if b is not None else grad_sinks(w)
         return y.view(*x.shape[:-1], w.shape[0])
 
     @staticmethod
@@ -38,7 +38,9 @@ class _LinearFn(torch.autograd.Function):
             dx = torch.zeros_like(x2)
             ops.skinny_nn(dy2.unsqueeze(0), w.unsqueeze(0), dx.unsqueeze(0))
             dx = dx.view(ctx.xshape)
-        if ctx.needs_input_grad[1] or ctx.has_bias:
+        if ctx.sinks is not None:
+            ops.skinny_outer(dy2.unsqueeze(0), x2.unsqueeze(0), into=ctx.sinks[0], colsum_into=ctx.sinks[1] if ctx.has_bias else None)
+        elif ctx.needs_input_grad[1] or ctx.has_bias:
             dw, db = ops.skinny_outer(dy2.unsqueeze(0), x2.unsqueeze(0), want_colsum=ctx.has_bias)
             dw = dw[0]
             db = db[0] if ctx.has_bias else None
@@ -47,9 +49,11 @@ class _LinearFn(torch.autograd.Function):
 
 def linear(x, w, b=None):
     """F.linear for fp32 slot rows"""
-    rows = x.numel() // x.shape[-1]
-    if rows > MAX_ROWS or x.dtype != torch.float32 or w.shape[1] % 4 != 0:
-        return F.linear(x, w, b)
+    if not x.is_cuda:
+        raise RuntimeError('devias_b200.slot_linear runs on CUDA only (no CPU fallback)')
+    if x.dtype != torch.float32:
+        x = x.float()
+    assert w.shape[1] % 4 == 0, 'slot-row products need an input width that is a multiple of 4'
     return _LinearFn.apply(x, w, b)
 
 
@@ -64,6 +68,7 @@ class _FoldKeysFn(torch.autograd.Function):
         qt = torch.zeros(B, H, S, D, device=q.device, dtype=torch.float32)
         ops.skinny_nn(q.permute(2, 0, 1, 3), wk.view(H, dh, D), qt.permute(1, 0, 2, 3))
         ctx.save_for_backward(q, wk)
+        ctx.sinks = grad_sinks(wk)
         return qt
 
     @staticmethod
@@ -74,6 +79,9 @@ class _FoldKeysFn(torch.autograd.Function):
         dqt = dqt.contiguous()
         dq = torch.empty_like(q)
         ops.skinny_nt(dqt.permute(1, 0, 2, 3), wk.view(H, dh, D), None, dq.permute(2, 0, 1, 3))
+        if ctx.sinks is not None:
+            ops.skinny_outer(q.permute(2, 0, 1, 3), dqt.permute(1, 0, 2, 3), into=ctx.sinks[0])
+            return dq, None
         dwk, _ = ops.skinny_outer(q.permute(2, 0, 1, 3), dqt.permute(1, 0, 2, 3))
         return dq, dwk.view(H * dh, D)
 
@@ -89,6 +97,7 @@ class _ApplyValuesFn(torch.autograd.Function):
         out = torch.empty(B, S, H, dh, device=cbar.device, dtype=torch.float32)
         ops.skinny_nt(cbar.permute(1, 0, 2, 3), wv.view(H, dh, D), None, out.permute(2, 0, 1, 3))
         ctx.save_for_backward(cbar, wv)
+        ctx.sinks = grad_sinks(wv)
         return out.view(B, S, H * dh)
 
     @staticmethod
@@ -99,21 +108,18 @@ class _ApplyValuesFn(torch.autograd.Function):
         dout = dout.contiguous().view(B, S, H, dh)
         dcbar = torch.zeros_like(cbar)
         ops.skinny_nn(dout.permute(2, 0, 1, 3), wv.view(H, dh, D), dcbar.permute(1, 0, 2, 3))
+        if ctx.sinks is not None:
+            ops.skinny_outer(dout.permute(2, 0, 1, 3), cbar.permute(1, 0, 2, 3), into=ctx.sinks[0])
+            return dcbar, None
         dwv, _ = ops.skinny_outer(dout.permute(2, 0, 1, 3), cbar.permute(1, 0, 2, 3))
         return dcbar, dwv.view(H * dh, D)
 
 
 def fold_keys(q, wk):
-    B, S, H, dh = q.shape
-    if B * S > MAX_ROWS:
-        return torch.einsum('bshd,hdc->bhsc', q, wk.view(H, dh, -1))
     return _FoldKeysFn.apply(q, wk)
 
 
 def apply_values(cbar, wv):
-    B, H, S, D = cbar.shape
-    if B * S > MAX_ROWS:
-        return torch.einsum('bhsc,hdc->bshd', cbar, wv.view(H, -1, D)).reshape(B, S, -1)
     return _ApplyValuesFn.apply(cbar, wv)
 
 
@@ -135,6 +141,7 @@ class _FoldEpilogueFn(torch.autograd.Function):
                                                G.data_ptr(), c0.data_ptr(), R, D, ops.stream()), 'slot_fold_fwd')
         ctx.save_for_backward(qt, gamma, beta)
         ctx.scale = float(scale)
+        ctx.sinks = grad_sinks(gamma, beta)
         return g, G, c0
 
     @staticmethod
@@ -147,10 +154,13 @@ class _FoldEpilogueFn(torch.autograd.Function):
         dG = z((B, H * S)) if dG is None else dG.contiguous()
         dc0 = z((B, H * S)) if dc0 is None else dc0.contiguous()
         dqt = torch.empty_like(qt)
-        dgb = torch.zeros(2, D, device=qt.device, dtype=torch.float32)
+        direct = ctx.sinks is not None
+        dgb = ctx.sinks if direct else torch.zeros(2, D, device=qt.device, dtype=torch.float32)
         ops.check(ops.L().devias_slot_fold_bwd(qt.data_ptr(), gamma.data_ptr(), beta.data_ptr(), ctx.scale, dg.data_ptr(), dG.data_ptr(),
                                                dc0.data_ptr(), dqt.data_ptr(), dgb[0].data_ptr(), dgb[1].data_ptr(), R, D, ops.stream()),
                   'slot_fold_bwd')
+        if direct:
+            return dqt, None, None, None
         return dqt, dgb[0], dgb[1], None
 
 
@@ -166,6 +176,7 @@ class _ContextFn(torch.autograd.Function):
                                               cbar.data_ptr(), B * HS, D, ops.stream()), 'slot_ctx_fwd')
         ctx.save_for_backward(U, m, A, gamma, beta)
         ctx.eps = float(eps)
+        ctx.sinks = grad_sinks(gamma, beta)
         return cbar
 
     @staticmethod
@@ -175,10 +186,13 @@ class _ContextFn(torch.autograd.Function):
         dcbar = dcbar.contiguous()
         dU = torch.empty_like(U)
         dmA = torch.empty(2, B, HS, device=U.device, dtype=torch.float32)
-        dgb = torch.zeros(2, D, device=U.device, dtype=torch.float32)
+        direct = ctx.sinks is not None
+        dgb = ctx.sinks if direct else torch.zeros(2, D, device=U.device, dtype=torch.float32)
         ops.check(ops.L().devias_slot_ctx_bwd(dcbar.data_ptr(), U.data_ptr(), m.data_ptr(), A.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
                                               ctx.eps, dU.data_ptr(), dmA[0].data_ptr(), dmA[1].data_ptr(), dgb[0].data_ptr(),
                                               dgb[1].data_ptr(), B * HS, D, ops.stream()), 'slot_ctx_bwd')
+        if direct:
+            return dU, dmA[0], dmA[1], None, None, None
         return dU, dmA[0], dmA[1], dgb[0], dgb[1], None
 
 
@@ -188,3 +202,89 @@ def fold_epilogue(qt, gamma, beta, scale):
 
 def context(U, m, A, gamma, beta, eps=1e-7):
     return _ContextFn.apply(U, m, A, gamma, beta, eps)
+
+
+class _SlotLayerNormFn(torch.autograd.Function):
+    """nn.LayerNorm on fp32 slot rows (agg_block/attention.py:29-30,35; agg_block/agg_block.py:111) through the LayerNorm kernels
+    of csrc/layernorm.cu instead of the ATen ones; gamma / beta gradients accumulate in place."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        x = x.contiguous()
+        y, mean, rstd = ops.layernorm_fwd(x, weight, bias, eps, torch.float32)
+        ctx.save_for_backward(x, mean, rstd, weight)
+        ctx.sinks = grad_sinks(weight, bias)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, mean, rstd, weight = ctx.saved_tensors
+        direct = ctx.sinks is not None
+        dgb = ctx.sinks if direct else torch.zeros(2, weight.numel(), device=x.device, dtype=torch.float32)
+        dx, _ = ops.layernorm_bwd(dy.contiguous(), x, mean, rstd, weight, want_bf16=False, dgamma=dgb[0], dbeta=dgb[1])
+        if direct:
+            return dx, None, None, None
+        return dx, dgb[0], dgb[1], None
+
+
+def layer_norm(x, norm: torch.nn.LayerNorm):
+    """`norm(x)` for fp32 CUDA slot rows of width 768"""
+    if x.shape[-1] != 768 or not norm.elementwise_affine:
+        raise NotImplementedError('the LayerNorm kernels are instantiated for width 768 with affine parameters (DEVIAS slot dim)')
+    return _SlotLayerNormFn.apply(x.float(), norm.weight, norm.bias, norm.eps)
+
+
+class _BmmNTFn(torch.autograd.Function):
+    """y[z] = x[z] w[z]^T   (x [Z, M, K], w [Z, N, K]) -> [Z, M, N]; both operands may need gradients"""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        x, w = x.contiguous(), w.contiguous()
+        y = torch.empty(x.shape[0], x.shape[1], w.shape[1], device=x.device, dtype=torch.float32)
+        ops.skinny_nt(x, w, None, y)
+        ctx.save_for_backward(x, w)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.zeros_like(x)
+            ops.skinny_nn(dy, w, dx)
+        if ctx.needs_input_grad[1]:
+            dw, _ = ops.skinny_outer(dy, x)
+        return dx, dw
+
+
+class _BmmNNFn(torch.autograd.Function):
+    """y[z] = x[z] w[z]   (x [Z, M, K], w [Z, K, N]) -> [Z, M, N]"""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        x, w = x.contiguous(), w.contiguous()
+        y = torch.zeros(x.shape[0], x.shape[1], w.shape[2], device=x.device, dtype=torch.float32)
+        ops.skinny_nn(x, w, y)
+        ctx.save_for_backward(x, w)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            ops.skinny_nt(dy, w, None, dx)
+        if ctx.needs_input_grad[1]:
+            dw, _ = ops.skinny_outer(x, dy)
+        return dx, dw
+
+
+def bmm_nt(x, w):
+    return _BmmNTFn.apply(x, w)
+
+
+def bmm_nn(x, w):
+    return _BmmNNFn.apply(x, w)

@@ -37,6 +37,13 @@ int64_t devias_launch_count(void);
 #define DEVIAS_PROF_SLOT 2
 #define DEVIAS_PROF_NORM 3
 int devias_profile_begin(void);
+/* same, but only launches made inside a CUDA stream capture are bracketed (eager warm-up launches are ignored) */
+int devias_profile_begin_capture(void);
+/* stop bracketing new launches; the records made so far stay readable */
+int devias_profile_pause(void);
+/* When the launches were made inside a CUDA stream capture, the brackets are external event-record nodes of the captured graph:
+ * after every replay, end() returns the times of that replay (kernels timed INSIDE the replayed step).  It may be called
+ * repeatedly; it never discards the records (begin() does). */
 int devias_profile_end(int kind, double* total_ms, double* total_work, int64_t* launches);
 
 /* ---- GEMM on tcgen05/TMEM fed by TMA ------------------------------------------------------------
@@ -102,7 +109,8 @@ int devias_slot_stream_fwd(const float* tokens, const float* g, const float* G, 
 
 /* Backward of devias_slot_stream_fwd.  attn / mu / rstd are the forward's outputs; dU, dm, dA (and optionally dattn) the
  * upstream gradients.  Writes dtokens [batch, n_tokens, 768] (accumulate_dtokens != 0: +=, used to sum the layers of the
- * aggregation block in place) and ACCUMULATES dg [batch, 4*S, 768], dG, dc0 [batch, 4*S].  S in {2, 4}. */
+ * aggregation block in place) and ACCUMULATES dg [batch, 4*S, 768], dG, dc0 [batch, 4*S].  S in {2, 4, 8} (S = 8 runs as two
+ * passes over two heads each). */
 int devias_slot_stream_bwd(const float* tokens, const float* mu, const float* rstd, const float* g, const float* G,
                            const float* attn, const float* dU, const float* dm, const float* dA, const float* dattn,
                            float* dtokens, int accumulate_dtokens, float* dg, float* dG, float* dc0, int batch, int n_tokens,
@@ -173,13 +181,32 @@ int devias_debug_token_stream(const float* tokens, int batch, int n_tokens, int 
  *   nt    : y[m, n]  = sum_k x[m, k] w[n, k] (+ bias[n])    w [N, K] row-major; K % 4 == 0
  *   nn    : y[m, n] += sum_k x[m, k] w[k, n]                w [K, N] row-major; y is accumulated (caller pre-fills it)
  *   outer : c[i, j]  = sum_m a[m, i] b[m, j]                c [I, J] row-major, J % 4 == 0; colsum[i] = sum_m a[m, i] if
- *                                                           colsum != NULL (the bias gradient when a = dY) */
+ *                                                           colsum != NULL (the bias gradient when a = dY);
+ *                                                           accumulate != 0: c and colsum are added to (+=) -- weight-tied layers
+ *                                                           summing into the gradient arena */
 int devias_skinny_nt(const float* x, const int64_t* x_map, const float* w, int64_t w_batch, const float* bias, float* y,
                      const int64_t* y_map, int M, int N, int K, int batch, void* stream);
 int devias_skinny_nn(const float* x, const int64_t* x_map, const float* w, int64_t w_batch, float* y, const int64_t* y_map,
                      int M, int N, int K, int batch, void* stream);
 int devias_skinny_outer(const float* a, const int64_t* a_map, const float* b, const int64_t* b_map, float* c, int64_t c_batch,
-                        float* colsum, int64_t colsum_batch, int M, int I, int J, int batch, void* stream);
+                        float* colsum, int64_t colsum_batch, int M, int I, int J, int batch, int accumulate, void* stream);
+
+/* ---- optimizer update over the flat parameter arena --------------------------------------------------------------
+ * AdamW exactly as torch.optim.AdamW (the optimizer utils/optim_factory.py:94-178 builds; stepped at
+ * engine/engine_for_slot.py:147-166), applied in ONE pass over flat fp32 arenas {param, grad, exp_avg, exp_avg_sq} of n
+ * elements (n % 8 == 0): the pass also refreshes the bf16 copies the tensor-core kernels read (param_bf16, may be NULL) and
+ * zero-fills the gradient (zero_grad != 0), replacing the multi-tensor optimizer launches, the weight cast and the memset.
+ * Parameters occupy segments of 8-element granules: seg_start[0..n_seg] (device int32, ascending, seg_start[n_seg] = n / 8),
+ * seg_group[s] = hyper-parameter group of segment s.  All hyper-parameters are read from DEVICE memory (so a captured CUDA
+ * graph follows the learning-rate / weight-decay schedule written every iteration at engine/engine_for_slot.py:91-97):
+ *   hyper[0] = 1 - beta1^t, [1] = 1 - beta2^t, [2] = beta1, [3] = beta2, [4] = eps, [5] = max_norm (<= 0: off),
+ *   [6] = gradient pre-scale, [7] unused, then per group g: [8 + 2g] = lr, [9 + 2g] = weight_decay.
+ * grad_sumsq (device fp32 scalar, may be NULL): sum of squares of the whole gradient arena (devias_sumsq_f32); with
+ * max_norm > 0 the gradient is scaled by min(1, max_norm / (|pre-scale| * sqrt(sumsq) + 1e-6)) = torch clip_grad_norm_. */
+int devias_sumsq_f32(const float* x, int64_t n, float* out, void* stream);
+int devias_adamw_arena(float* param, float* grad, float* exp_avg, float* exp_avg_sq, void* param_bf16,
+                       const int32_t* seg_start, const int32_t* seg_group, int n_seg, const float* hyper,
+                       const float* grad_sumsq, int64_t n, int zero_grad, void* stream);
 
 #ifdef __cplusplus
 }

@@ -138,3 +138,79 @@ def test_range_exchange_world2_matches_single_process():
     for a, b0, b1 in zip(m.parameters(), res[0][1], res[1][1]):
         assert torch.allclose(a.grad, torch.from_numpy(b0), atol=1e-6) and (b0 == b1).all()
     assert res[0][2] and res[1][2]
+
+
+class _ToyStudent(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.net = _model()
+
+    def forward(self, x):
+        return self.net(x)
+
+
+def _toy_criterion(model, student_output, teacher_output, target, fg_mask=None):
+    loss = ((student_output - target) ** 2).mean()
+    return loss, student_output, {}
+
+
+def _worker_accumulate(rank, world, port, q):
+    """gradient accumulation driven THROUGH engine.train_step with a reducer (update_freq = 2)"""
+    from devias_b200 import engine
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        m = _ToyStudent()
+        red = GradReducer(m, bucket_mb=0.004, first_bucket_mb=0.001)
+        opt = torch.optim.SGD(m.parameters(), lr=0.1)
+        g = torch.Generator().manual_seed(1)
+        x = torch.randn(16, 37, generator=g); y = torch.randn(16, 19, generator=g)
+        xs, ys = x.chunk(world)[rank], y.chunk(world)[rank]
+        for it in range(2):                                   # two optimizer steps, each of two micro-steps
+            for u in range(2):
+                sl = slice(4 * u, 4 * u + 4)
+                engine.train_step(m, None, _toy_criterion, opt, xs[sl], ys[sl], None, teacher_logits=ys[sl], update_freq=2,
+                                  do_update=(u == 1), reducer=red)
+        q.put((rank, [p.detach().clone().numpy() for p in m.parameters()]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_accumulation_through_train_step_world2_matches_single_process():
+    world, port = 2, _free_port()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_accumulate, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for p0, p1 in zip(res[0][1], res[1][1]):
+        assert (p0 == p1).all(), 'ranks diverged under gradient accumulation'
+    # single process: every optimizer step sees the mean gradient over the same 16 samples
+    m = _ToyStudent()
+    opt = torch.optim.SGD(m.parameters(), lr=0.1)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(16, 37, generator=g); y = torch.randn(16, 19, generator=g)
+    for it in range(2):
+        opt.zero_grad()
+        ((m(x) - y) ** 2).mean().backward()
+        opt.step()
+    for a, b0 in zip(m.parameters(), res[0][1]):
+        assert torch.allclose(a.detach(), torch.from_numpy(b0), atol=1e-6)
+
+
+def test_finish_raises_when_exchange_is_off():
+    """a reducer whose exchange is switched off must not silently let the ranks step on local gradients"""
+    m = _model()
+    red = GradReducer(m)
+    red.world = 2                     # pretend: no process group is needed to reach the check
+    red.enabled = False
+    try:
+        red.finish()
+        raised = False
+    except RuntimeError:
+        raised = True
+    assert raised

@@ -67,3 +67,86 @@ def test_graphed_steps_match_eager():
             d = (other[k] - ref[k]).abs().max().item()
             scale = ref[k].abs().max().item() + 1e-6
             assert d <= 2e-3 * scale + 2e-5, (name, k, d, scale)
+
+
+def _adamw_groups(m, lr):
+    decay = [p for p in m.parameters() if p.dim() > 1]
+    rest = [p for p in m.parameters() if p.dim() <= 1]
+    return [dict(params=decay, weight_decay=0.05, lr=lr), dict(params=rest, weight_decay=0.0, lr=lr)]
+
+
+@pytest.mark.parametrize('update_freq,max_norm', [(1, 0.0), (2, 0.5)])
+def test_arena_graphed_step_follows_schedule_and_matches_eager_torch_adamw(update_freq, max_norm):
+    """arena mode (ArenaAdamW + direct gradient accumulation, update in its own graph) against the eager step with
+    torch.optim.AdamW: the learning rate changes EVERY optimizer step (the captured graph must follow it), gradients are
+    accumulated over `update_freq` micro-batches and clipped to `max_norm` (engine/engine_for_slot.py:91-97, 147-166)."""
+    from devias_b200 import engine
+    from devias_b200.arena import ParamArena
+    from devias_b200.loss import TrainLoss
+    from devias_b200.optim import ArenaAdamW
+    C = 11
+    bs = [_batch(C), _batch(C)]
+    bs[1]['clip'] = O.synth_clips(2, seed=9).cuda()
+    crit = TrainLoss(None, 'KL', C)
+    lrs = [2e-3, 1e-3, 3e-3]
+
+    m = _model(C)
+    opt = torch.optim.AdamW(_adamw_groups(m, lrs[0]), betas=(0.9, 0.999), eps=1e-8)
+    micro = 0
+    for lr in lrs:
+        for g in opt.param_groups:
+            g['lr'] = lr
+        for u in range(update_freq):
+            b = bs[micro % 2]; micro += 1
+            engine.train_step(m, None, crit, opt, b['clip'], b['target'], (b['fg'], b['fgf']), teacher_logits=b['teacher'],
+                              update_freq=update_freq, do_update=(u == update_freq - 1), max_norm=max_norm)
+    ref = _params(m)
+
+    m2 = _model(C)
+    opt2 = ArenaAdamW(_adamw_groups(m2, lrs[0]), ParamArena.of(m2), betas=(0.9, 0.999), eps=1e-8, max_norm=max_norm)
+    snap = copy.deepcopy(m2.state_dict())
+    step = engine.GraphedTrainStep(m2, crit, opt2, bs, warmup=1, update_freq=update_freq)
+    m2.load_state_dict(snap)
+    opt2.exp_avg.zero_(); opt2.exp_avg_sq.zero_(); opt2._t = 0; opt2.arena.grad.zero_()
+    micro = 0
+    for lr in lrs:
+        for g in opt2.param_groups:
+            g['lr'] = lr
+        for u in range(update_freq):
+            loss = step(micro % 2); micro += 1
+    torch.cuda.synchronize()
+    assert torch.isfinite(loss)
+    got = _params(m2)
+    # compare the parameter UPDATES (Adam normalises them to ~lr per element, so following the lr schedule, the accumulation
+    # and the clipping all show up in their size); the two paths run the same kernels, differences are atomics-order noise
+    # amplified by Adam's normalisation of near-zero gradients
+    du_ref = torch.cat([(ref[k] - snap[k].cuda()).flatten() for k in ref]).double()
+    du_got = torch.cat([(got[k] - snap[k].cuda()).flatten() for k in ref]).double()
+    rel = float((du_got - du_ref).norm() / du_ref.norm())
+    assert rel <= 0.05, rel
+    assert float(du_ref.abs().max()) > 0.5 * min(lrs)
+
+
+def test_graphed_step_leaves_reducer_and_model_usable_for_eager_steps():
+    """GraphedTrainStep must not leave the shared reducer switched off nor its cut-point hook active"""
+    from devias_b200 import engine
+    from devias_b200.ddp import GradReducer
+    from devias_b200.loss import TrainLoss
+    C = 11
+    b = _batch(C)
+    crit = TrainLoss(None, 'KL', C)
+    m = _model(C)
+    red = GradReducer(m)
+    opt = torch.optim.SGD(m.parameters(), lr=0.01)
+    step = engine.GraphedTrainStep(m, crit, opt, [b], reducer=red, warmup=1, cuts=[3, 1])
+    assert len(step.graphs[0]) == 3                      # two cuts -> three backward pieces
+    step(0)
+    assert red.enabled is True
+    step.close()
+    assert not step._hooks
+    before = _params(m)
+    engine.train_step(m, None, crit, opt, b['clip'], b['target'], (b['fg'], b['fgf']), teacher_logits=b['teacher'], reducer=red)
+    torch.cuda.synchronize()
+    after = _params(m)
+    assert any(not torch.equal(before[k], after[k]) for k in before)
+    assert not step._taps

@@ -31,7 +31,8 @@ def test_slot_stream_fwd(B, N, S):
     assert torch.allclose(attn.view(B, 4, S, N).sum(2), torch.ones(B, 4, N, device='cuda'), atol=1e-5)
 
 
-@pytest.mark.parametrize('B,N,S,with_dattn', [(2, 1568, 2, True), (3, 1568, 4, False), (2, 100, 2, True), (1, 1569, 2, False)])
+@pytest.mark.parametrize('B,N,S,with_dattn', [(2, 1568, 2, True), (3, 1568, 4, False), (2, 100, 2, True), (1, 1569, 2, False),
+                                               (2, 1568, 8, True), (1, 100, 8, False)])
 def test_slot_stream_bwd(B, N, S, with_dattn):
     """streaming backward kernel vs float64 autograd of the same folded contract"""
     from devias_b200 import ops, slot_attention as SA
