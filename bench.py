@@ -375,14 +375,22 @@ def slot_grid(dev, peak_gbs):
     from devias_b200 import ops
 
     def timeit(fn, n):
-        for _ in range(2):
-            fn()
+        """ms per call; warm-up and timed region are both >= ~40 ms long so that the SM clock has settled on this (memory-bound)
+        load after the power-capped GEMM phases that ran before"""
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize(); s0.record()
-        for _ in range(n):
+        for _ in range(3):
             fn()
         s1.record(); torch.cuda.synchronize()
-        return s0.elapsed_time(s1) / n
+        per = max(s0.elapsed_time(s1) / 3, 1e-3)
+        reps = int(min(max(n, 40.0 / per), 2000))
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize(); s0.record()
+        for _ in range(reps):
+            fn()
+        s1.record(); torch.cuda.synchronize()
+        return s0.elapsed_time(s1) / reps
 
     out = []
     for dt in (torch.float32, torch.bfloat16):

@@ -410,7 +410,7 @@ def train_loss(student_output, teacher_scene_logit: Tensor, target: Tensor, fg_m
     mask_predictions = mask_predictions.reshape(bs, S, -1)
     scene_target = torch.argmax(teacher_scene_logit, dim=1) + num_action_classes
     var = teacher_scene_logit.min() - 1.0
-    teacher_full = torch.cat([torch.full((bs, num_action_classes), float(var)), teacher_scene_logit], dim=1)
+    teacher_full = torch.cat([torch.full((bs, num_action_classes), float(var), device=teacher_scene_logit.device), teacher_scene_logit], dim=1)
     sfm = slots_head.softmax(-1)
     slots_head = slots_head.view(bs, S, -1)
     fg, fg_frames = fg_mask
@@ -431,7 +431,7 @@ def train_loss(student_output, teacher_scene_logit: Tensor, target: Tensor, fg_m
                                                reduction='batchmean', log_target=True) * scene_loss_weight
     action_loss, scene_loss, mp_loss, md_loss = (t / bs for t in (action_loss, scene_loss, mp_loss, md_loss))
     sl = F.normalize(slots.reshape(bs, S, -1), p=2, dim=2)
-    cs = torch.bmm(sl, sl.transpose(1, 2)) * (1 - torch.eye(S))
+    cs = torch.bmm(sl, sl.transpose(1, 2)) * (1 - torch.eye(S, device=sl.device))
     cosine_loss = (cs.sum(dim=(1, 2)) / (S * (S - 1))).mean()
     total = action_loss + scene_loss + cosine_loss + mp_loss + md_loss
     parts = dict(action_loss=action_loss, scene_loss=scene_loss, cosine_loss=cosine_loss,

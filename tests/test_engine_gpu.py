@@ -123,7 +123,9 @@ def test_arena_graphed_step_follows_schedule_and_matches_eager_torch_adamw(updat
     du_ref = torch.cat([(ref[k] - snap[k].cuda()).flatten() for k in ref]).double()
     du_got = torch.cat([(got[k] - snap[k].cuda()).flatten() for k in ref]).double()
     rel = float((du_got - du_ref).norm() / du_ref.norm())
-    assert rel <= 0.05, rel
+    worst = sorted(((float(((got[k] - ref[k]).double().norm()) / (float((ref[k] - snap[k].cuda()).double().norm()) + 1e-12)), k)
+                    for k in ref), reverse=True)[:6]
+    assert rel <= 0.05, (rel, worst)
     assert float(du_ref.abs().max()) > 0.5 * min(lrs)
 
 
