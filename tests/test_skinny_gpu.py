@@ -30,13 +30,24 @@ def test_linear_matches_torch(M, K, N, bias):
         assert a.shape == r.shape and _rel(a, r) < 2e-6
 
 
-def test_linear_3d_input_and_large_rows_fallback():
-    from devias_b200 import slot_linear
+@pytest.mark.parametrize('rows', [33, 64, 512, 1000])
+def test_linear_3d_input_and_any_number_of_rows(rows):
+    """no row limit and no library GEMM behind slot_linear: K400 B = 32 has 64 slot rows, an evaluation batch of 256 has 512"""
+    from devias_b200 import _lib, slot_linear
     x = torch.randn(8, 2, 768, device='cuda')
-    w = torch.randn(512, 768, device='cuda') * 0.05
+    w = (torch.randn(512, 768, device='cuda') * 0.05).requires_grad_(True)
+    b = torch.randn(512, device='cuda', requires_grad=True)
     assert _rel(slot_linear.linear(x, w), F.linear(x.double(), w.double())) < 2e-6
-    xl = torch.randn(slot_linear.MAX_ROWS + 1, 768, device='cuda')
-    assert _rel(slot_linear.linear(xl, w), F.linear(xl.double(), w.double())) < 1e-5
+    xl = torch.randn(rows, 768, device='cuda', requires_grad=True)
+    n0 = _lib.launch_count()
+    y = slot_linear.linear(xl, w, b)
+    dy = torch.randn_like(y)
+    gx, gw, gb = torch.autograd.grad(y, [xl, w, b], dy)
+    assert _lib.launch_count() - n0 == 3, 'forward + two backward kernels of csrc/skinny.cu'
+    xd, wd, bd = (t.detach().double().requires_grad_(True) for t in (xl, w, b))
+    yr = F.linear(xd, wd, bd)
+    rx, rw, rb = torch.autograd.grad(yr, [xd, wd, bd], dy.double())
+    assert _rel(y, yr) < 2e-6 and _rel(gx, rx) < 2e-6 and _rel(gw, rw) < 2e-6 and _rel(gb, rb) < 2e-6
 
 
 @pytest.mark.parametrize('B,S', [(8, 2), (1, 2), (3, 4), (32, 2), (5, 8)])
