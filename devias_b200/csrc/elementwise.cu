@@ -9,6 +9,8 @@ namespace dv {
 
 __global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out,
                                                             long long n8, long long n) {
+  pdl_trigger();
+  pdl_wait();
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
     const float4 a = __ldcs(reinterpret_cast<const float4*>(in) + 2 * i);
@@ -22,6 +24,8 @@ __global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restr
 __global__ void __launch_bounds__(256) scale_rows_cast_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out,
                                                               long long n8, int cols8, const float* __restrict__ row_scale,
                                                               int rows_per_scale) {
+  pdl_trigger();
+  pdl_wait();
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
     const float s = __ldg(row_scale + (i / cols8) / rows_per_scale);
@@ -61,6 +65,8 @@ __device__ __forceinline__ void load8<__half>(const __half* p, float (&v)[8]) {
 template <typename T>
 __global__ void __launch_bounds__(256) patchify_kernel(const T* __restrict__ clip, __nv_bfloat16* __restrict__ out, int B, int C,
                                                        int F, int H, int W) {
+  pdl_trigger();
+  pdl_wait();
   const int segs = W / 8;
   const long long total = (long long)B * C * F * H * segs;
   const int hp = H / 16, wp = W / 16, tp = F / 2;
@@ -93,7 +99,7 @@ extern "C" int devias_cast_f32_bf16(const float* in, void* out, int64_t n, void*
   long long blocks = (n8 + 255) / 256;
   if (blocks > sm_count() * 16) blocks = sm_count() * 16;
   if (blocks < 1) blocks = 1;
-  cast_f32_bf16_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(in, static_cast<__nv_bfloat16*>(out), n8, n);
+  DV_CHECK_CUDA(launch_k(cast_f32_bf16_kernel, dim3((unsigned)((int)blocks)), dim3((unsigned)(256)), (size_t)(0), static_cast<cudaStream_t>(stream), in, static_cast<__nv_bfloat16*>(out), n8, n));
   DV_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return DEVIAS_OK;
@@ -108,8 +114,8 @@ extern "C" int devias_scale_rows_cast(const float* in, void* out, int rows, int 
   const long long n8 = (long long)rows * cols / 8;
   long long blocks = (n8 + 255) / 256;
   if (blocks > sm_count() * 16) blocks = sm_count() * 16;
-  scale_rows_cast_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(in, static_cast<__nv_bfloat16*>(out), n8,
-                                                                                   cols / 8, row_scale, rows_per_scale);
+  DV_CHECK_CUDA(launch_k(scale_rows_cast_kernel, dim3((unsigned)((int)blocks)), dim3((unsigned)(256)), (size_t)(0), static_cast<cudaStream_t>(stream), in, static_cast<__nv_bfloat16*>(out), n8,
+                                                                                   cols / 8, row_scale, rows_per_scale));
   DV_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return DEVIAS_OK;
@@ -128,9 +134,9 @@ extern "C" int devias_patchify(const void* clip, int clip_dtype, void* out, int 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
   switch (clip_dtype) {
-    case DEVIAS_DTYPE_F32: patchify_kernel<float><<<(int)blocks, 256, 0, s>>>(static_cast<const float*>(clip), o, batch, chans, frames, height, width); break;
-    case DEVIAS_DTYPE_BF16: patchify_kernel<__nv_bfloat16><<<(int)blocks, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(clip), o, batch, chans, frames, height, width); break;
-    case DEVIAS_DTYPE_F16: patchify_kernel<__half><<<(int)blocks, 256, 0, s>>>(static_cast<const __half*>(clip), o, batch, chans, frames, height, width); break;
+    case DEVIAS_DTYPE_F32: DV_CHECK_CUDA(launch_k(patchify_kernel<float>, dim3((unsigned)((int)blocks)), dim3((unsigned)(256)), (size_t)(0), s, static_cast<const float*>(clip), o, batch, chans, frames, height, width)); break;
+    case DEVIAS_DTYPE_BF16: DV_CHECK_CUDA(launch_k(patchify_kernel<__nv_bfloat16>, dim3((unsigned)((int)blocks)), dim3((unsigned)(256)), (size_t)(0), s, static_cast<const __nv_bfloat16*>(clip), o, batch, chans, frames, height, width)); break;
+    case DEVIAS_DTYPE_F16: DV_CHECK_CUDA(launch_k(patchify_kernel<__half>, dim3((unsigned)((int)blocks)), dim3((unsigned)(256)), (size_t)(0), s, static_cast<const __half*>(clip), o, batch, chans, frames, height, width)); break;
     default: set_last_error("clip_dtype", "unknown dtype id", __FILE__, __LINE__); return DEVIAS_ERR_ARG;
   }
   DV_CHECK_CUDA(cudaGetLastError());

@@ -29,7 +29,6 @@ struct GemmParams {
   const float* bias;
   int aux_row_mod;
   const float* row_scale; int rows_per_scale;
-  float* delta; int seq, npad, heads;   // DELTA_BF16: delta[(b * heads + col / 64) * npad + n] = sum_64 out * aux  (row = b * seq + n)
 };
 
 constexpr int kBM = 128;
@@ -40,7 +39,7 @@ constexpr int kBoxBytes = 32 * 128; // one epilogue staging box: 32 rows x 128 B
 template <int EPI>
 struct EpiTraits {
   static constexpr bool OUT_F32 = EPI == DEVIAS_EPI_STORE_F32 || EPI == DEVIAS_EPI_RESID_F32 || EPI == DEVIAS_EPI_ATOMIC_F32;
-  static constexpr bool HAS_AUX = EPI == DEVIAS_EPI_RESID_F32 || EPI == DEVIAS_EPI_DGELU_BF16 || EPI == DEVIAS_EPI_DELTA_BF16;
+  static constexpr bool HAS_AUX = EPI == DEVIAS_EPI_RESID_F32 || EPI == DEVIAS_EPI_DGELU_BF16;
   static constexpr bool TWO_OUT = EPI == DEVIAS_EPI_GELU_BF16;
   static constexpr int BOX_COLS = OUT_F32 ? 32 : 64;   // 128 bytes of output per row
   static constexpr int BOXES_PER_WARP_SMEM = (HAS_AUX || TWO_OUT) ? 2 : 1;
@@ -79,6 +78,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2,
                  const __grid_constant__ CUtensorMap tmAux, const GemmParams p) {
+  pdl_trigger();
   using Cfg = GemmCfg<BN, EPI>;
   using ET = EpiTraits<EPI>;
   extern __shared__ uint8_t smem_raw[];
@@ -128,6 +128,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   cluster_sync_all();      // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();              // everything above overlapped the previous kernel's tail; global memory is touched only below
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -286,7 +287,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               tmem_ld_32x32b_x32(taddr + b * 64 + hlf * 32, acc);
               tmem_ld_wait();
               const int cc = col0 + hlf * 32;
-              const bool has_bias = EPI != DEVIAS_EPI_DGELU_BF16 && EPI != DEVIAS_EPI_DELTA_BF16 && p.bias != nullptr && cc < p.N;
+              const bool has_bias = EPI != DEVIAS_EPI_DGELU_BF16 && p.bias != nullptr && cc < p.N;
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 float4 v = make_float4(__uint_as_float(acc[4 * i]), __uint_as_float(acc[4 * i + 1]), __uint_as_float(acc[4 * i + 2]),
@@ -309,19 +310,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                   outv2[hlf * 16 + 2 * i + 1] = pack_bf16(f2_lo(a1), f2_hi(a1));
                 }
               }
-            }
-          }
-          if constexpr (EPI == DEVIAS_EPI_DELTA_BF16) {
-            // flash-attention backward row term: delta[q, head] = sum_d dO[q, d] O[q, d] over this box (64 columns = one head)
-            float sdot = 0.f;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float2 dv_ = unpack_bf16(outv[i]), ov = unpack_bf16(aux[i]);
-              sdot = fmaf(dv_.x, ov.x, fmaf(dv_.y, ov.y, sdot));
-            }
-            if (row < p.M) {
-              const int bb = row / p.seq, nn = row - bb * p.seq;
-              p.delta[((long long)bb * p.heads + col0 / 64) * p.npad + nn] = sdot;
             }
           }
           // ---- staging box free again? (the previous bulk store of this warp has finished READING it)
@@ -409,7 +397,7 @@ static int launch_gemm(const GemmHostArgs& h, const GemmParams& p, cudaStream_t 
   const int max_clusters = sm_count() / 2;
   const int grid = 2 * (pair_tiles < max_clusters ? pair_tiles : max_clusters);
   const int prof = prof_begin(DEVIAS_PROF_GEMM, 2.0 * p.M * (double)p.N * p.K, stream);
-  kern<<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmOut, tmOut2, tmAux, p);
+  DV_CHECK_CUDA(launch_k(kern, dim3((unsigned)(grid)), dim3((unsigned)(kGemmThreads)), (size_t)(Cfg::SMEM_BYTES), stream, tmA, tmB, tmOut, tmOut2, tmAux, p));
   prof_end(prof, stream);
   DV_CHECK_CUDA(cudaGetLastError());
   count_launch();
@@ -463,7 +451,7 @@ extern "C" int devias_gemm_bf16(const void* a, int64_t lda, int a_mn_major, cons
     const int per = (k_blks + splits - 1) / splits;
     splits = (k_blks + per - 1) / per;
   }
-  GemmParams p{m, n, k, splits, bias, aux_row_mod, row_scale, rows_per_scale, nullptr, 0, 0, 0};
+  GemmParams p{m, n, k, splits, bias, aux_row_mod, row_scale, rows_per_scale};
   GemmHostArgs h{a, (long long)lda, b, (long long)ldb, out, (long long)ldo, out2, (long long)ldo2, aux, (long long)ldaux};
   // BN = 256 maximises operand reuse; fall back to 128 when that leaves too few tiles for the 74 clusters
   const int m_blks = (m + kBM - 1) / kBM;
@@ -482,24 +470,4 @@ extern "C" int devias_gemm_bf16(const void* a, int64_t lda, int a_mn_major, cons
   }
   set_last_error("epilogue", "unknown epilogue id", __FILE__, __LINE__);
   return DEVIAS_ERR_ARG;
-}
-
-// dO = dY W (the input gradient of Attention.proj, model/modeling_slot.py:113) with the flash-attention backward's row term
-// delta[b, h, q] = sum_d dO[b, q, h, d] * O[b, q, h, d] produced in the same epilogue (one 64-column box = one head).
-extern "C" int devias_gemm_dgrad_delta(const void* dy, int64_t ld_dy, const void* w, int64_t ldw, int w_mn_major, int m, int n,
-                                       int k, void* dout, int64_t ld_dout, const void* o_fwd, int64_t ld_o, float* delta,
-                                       int seq, int npad, int heads, void* stream) {
-  using namespace dv;
-  DV_REQUIRE(dy && w && dout && o_fwd && delta, "null operand");
-  DV_REQUIRE(m > 0 && n > 0 && k > 0 && seq > 0 && m % seq == 0 && npad >= seq, "bad sizes");
-  DV_REQUIRE(n == heads * 64, "n must be heads * 64 (one epilogue box per head)");
-  DV_REQUIRE(k % 8 == 0 && ld_dy % 8 == 0 && ldw % 8 == 0 && ld_dout % 8 == 0 && ld_o % 8 == 0, "leading dims must be multiples of 8");
-  DV_REQUIRE(((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(dout) |
-               reinterpret_cast<uintptr_t>(o_fwd)) & 15) == 0, "operands must be 16-byte aligned");
-  GemmParams p{m, n, k, 1, nullptr, 0, nullptr, 0, delta, seq, npad, heads};
-  GemmHostArgs h{dy, (long long)ld_dy, w, (long long)ldw, dout, (long long)ld_dout, nullptr, 0, o_fwd, (long long)ld_o};
-  const int m_blks = (m + kBM - 1) / kBM;
-  int bn = 256;
-  if (n % 256 != 0 || ((m_blks + 1) / 2) * (n / 256) < sm_count() / 2) bn = 128;
-  return dispatch_bn<DEVIAS_EPI_DELTA_BF16>(bn, false, w_mn_major != 0, h, p, static_cast<cudaStream_t>(stream));
 }

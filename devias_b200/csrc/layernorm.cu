@@ -18,6 +18,8 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
                                                             const float* __restrict__ beta, void* __restrict__ y,
                                                             float* __restrict__ mean, float* __restrict__ rstd, int M,
                                                             float eps) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int V = RowRegs<D>::V;
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -75,6 +77,8 @@ __global__ void __launch_bounds__(256, 3) layernorm_bwd_kernel(const void* __res
                                                                float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                                float* __restrict__ dx_colsum,
                                                                const float* __restrict__ bscale, int rows_per_scale, int M) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int V = RowRegs<D>::V;
   extern __shared__ float4 ln_acc[];                 // [3][8 warps][D/4]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
@@ -161,6 +165,8 @@ __global__ void __launch_bounds__(256, 3) layernorm_bwd_kernel(const void* __res
 // column sums of a bf16 [M,N] matrix into fp32 [N] (bias gradients of qkv / fc1): out[n] += sum_m a[m,n]
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ a, long long lda, int M, int N,
                                                           float* __restrict__ out, int rows_per_block) {
+  pdl_trigger();
+  pdl_wait();
   // thread handles 8 consecutive columns (one 16-byte load per row); block covers 32*8 = 256 columns x rows_per_block rows
   const int colgrp = blockIdx.x * 32 + (threadIdx.x & 31);
   const int col0 = colgrp * 8;
@@ -199,8 +205,8 @@ extern "C" int devias_layernorm_fwd(const float* x, const float* gamma, const fl
   if (rows <= 0) return DEVIAS_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int grid = (rows + 7) / 8;
-  if (y_is_bf16) layernorm_fwd_kernel<768, true><<<grid, 256, 0, s>>>(x, gamma, beta, y, mean, rstd, rows, eps);
-  else layernorm_fwd_kernel<768, false><<<grid, 256, 0, s>>>(x, gamma, beta, y, mean, rstd, rows, eps);
+  if (y_is_bf16) DV_CHECK_CUDA(launch_k(layernorm_fwd_kernel<768, true>, dim3(grid), dim3((unsigned)(256)), (size_t)(0), s, x, gamma, beta, y, mean, rstd, rows, eps));
+  else DV_CHECK_CUDA(launch_k(layernorm_fwd_kernel<768, false>, dim3(grid), dim3((unsigned)(256)), (size_t)(0), s, x, gamma, beta, y, mean, rstd, rows, eps));
   DV_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return DEVIAS_OK;
@@ -228,13 +234,13 @@ extern "C" int devias_layernorm_bwd(const void* dy, int dy_is_bf16, const float*
     attr_done = true;
   }
   if (dy_is_bf16)
-    layernorm_bwd_kernel<768, true><<<grid, 256, kLnSmem, s>>>(dy, x, mean, rstd, gamma, d_resid, dx,
+    DV_CHECK_CUDA(launch_k(layernorm_bwd_kernel<768, true>, dim3(grid), dim3((unsigned)(256)), (size_t)(kLnSmem), s, dy, x, mean, rstd, gamma, d_resid, dx,
                                                          static_cast<__nv_bfloat16*>(dx_bf16), dgamma, dbeta, dx_colsum, bf16_row_scale,
-                                                         rows_per_scale, rows);
+                                                         rows_per_scale, rows));
   else
-    layernorm_bwd_kernel<768, false><<<grid, 256, kLnSmem, s>>>(dy, x, mean, rstd, gamma, d_resid, dx,
+    DV_CHECK_CUDA(launch_k(layernorm_bwd_kernel<768, false>, dim3(grid), dim3((unsigned)(256)), (size_t)(kLnSmem), s, dy, x, mean, rstd, gamma, d_resid, dx,
                                                           static_cast<__nv_bfloat16*>(dx_bf16), dgamma, dbeta, dx_colsum, bf16_row_scale,
-                                                         rows_per_scale, rows);
+                                                         rows_per_scale, rows));
   DV_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return DEVIAS_OK;
@@ -247,8 +253,8 @@ extern "C" int devias_colsum_bf16(const void* a, int64_t lda, int rows, int cols
   if (rows <= 0) return DEVIAS_OK;
   const int rows_per_block = 128;   // 768 x 12544 -> 294 blocks (>= 1 per SM), 16 rows in flight per thread
   dim3 grid((cols + 255) / 256, (rows + rows_per_block - 1) / rows_per_block);
-  colsum_bf16_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(a), lda, rows, cols,
-                                                                         out, rows_per_block);
+  DV_CHECK_CUDA(launch_k(colsum_bf16_kernel, dim3(grid), dim3((unsigned)(256)), (size_t)(0), static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(a), lda, rows, cols,
+                                                                         out, rows_per_block));
   DV_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return DEVIAS_OK;

@@ -16,6 +16,8 @@ constexpr int MAX_SEGS = 1024;
 
 // sum of squares of the gradient arena -> *out (fp32, pre-zeroed); the clip coefficient is derived from it inside the update
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long long n4, float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   float acc = 0.f;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -41,6 +43,8 @@ __global__ void __launch_bounds__(256) adamw_arena_kernel(float* __restrict__ p,
                                                           const int* __restrict__ seg_start, const int* __restrict__ seg_group,
                                                           int n_seg, const float* __restrict__ hyper,
                                                           const float* __restrict__ sumsq, long long n8, int zero_grad) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ int s_start[MAX_SEGS + 1];
   __shared__ unsigned char s_group[MAX_SEGS];
   for (int i = threadIdx.x; i <= n_seg; i += blockDim.x) s_start[i] = seg_start[i];
@@ -112,7 +116,7 @@ extern "C" int devias_sumsq_f32(const float* x, int64_t n, float* out, void* str
   if (n <= 0) return DEVIAS_OK;
   long long blocks = (n / 4 + 255) / 256;
   if (blocks > sm_count() * 8) blocks = sm_count() * 8;
-  sumsq_kernel<<<(int)blocks, 256, 0, s>>>(x, n / 4, out);
+  DV_CHECK_CUDA(launch_k(sumsq_kernel, dim3((unsigned)((int)blocks)), dim3((unsigned)(256)), (size_t)(0), s, x, n / 4, out));
   DV_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return DEVIAS_OK;
@@ -131,9 +135,9 @@ extern "C" int devias_adamw_arena(float* param, float* grad, float* exp_avg, flo
   const long long n8 = n / 8;
   long long blocks = (n8 + 255) / 256;
   if (blocks > sm_count() * 8) blocks = sm_count() * 8;
-  adamw_arena_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  DV_CHECK_CUDA(launch_k(adamw_arena_kernel, dim3((unsigned)((int)blocks)), dim3((unsigned)(256)), (size_t)(0), static_cast<cudaStream_t>(stream), 
       param, grad, exp_avg, exp_avg_sq, static_cast<__nv_bfloat16*>(param_bf16), seg_start, seg_group, n_seg, hyper, grad_sumsq,
-      n8, zero_grad);
+      n8, zero_grad));
   DV_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return DEVIAS_OK;

@@ -17,6 +17,15 @@ void set_last_error(const char* what, const char* detail, const char* file, int 
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("DEVIAS_PDL");
+    on = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return on != 0;
+}
+
 int sm_count() {
   static int n = 0;
   if (n == 0) {

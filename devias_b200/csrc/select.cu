@@ -14,6 +14,8 @@ constexpr int kSelMaxSlots = 8;
 __global__ void __launch_bounds__(32 * kSelMaxSlots) slot_select_kernel(const float* __restrict__ logits, long long ld, int slots,
                                                                         int n_action, int n_scene, long long* __restrict__ a_idx,
                                                                         long long* __restrict__ s_idx) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float score[2][kSelMaxSlots];
   const int b = blockIdx.x, s = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = n_action + n_scene;
@@ -58,7 +60,7 @@ extern "C" int devias_slot_select(const float* logits, int64_t ld, int batch, in
   DV_REQUIRE(logits && action_idx && scene_idx, "null pointer");
   DV_REQUIRE(batch > 0 && slots > 0 && slots <= kSelMaxSlots, "slots must be 1..8");
   DV_REQUIRE(n_action > 0 && n_scene > 0 && ld >= n_action + n_scene, "bad class counts / row stride");
-  slot_select_kernel<<<batch, 32 * slots, 0, (cudaStream_t)stream>>>(logits, ld, slots, n_action, n_scene, action_idx, scene_idx);
+  DV_CHECK_CUDA(launch_k(slot_select_kernel, dim3((unsigned)(batch)), dim3((unsigned)(32 * slots)), (size_t)(0), (cudaStream_t)stream, logits, ld, slots, n_action, n_scene, action_idx, scene_idx));
   DV_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return DEVIAS_OK;

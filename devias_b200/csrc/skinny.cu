@@ -41,6 +41,8 @@ __device__ __forceinline__ void cp_async_wait_all() {
 __global__ void __launch_bounds__(256) skinny_nt_kernel(const float* __restrict__ x, RowMap xm, const float* __restrict__ w,
                                                         long long w_batch, const float* __restrict__ bias, float* __restrict__ y,
                                                         RowMap ym, int M, int N, int K) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float4 xs4[];                                  // [16][kc / 4]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nthreads = blockDim.x;
   const int z = blockIdx.z, m0 = blockIdx.y * kSkMT;
@@ -105,6 +107,8 @@ constexpr int kSkNnKS = 64;        // k rows per CTA
 __global__ void __launch_bounds__(kSkNnThreads) skinny_nn_kernel(const float* __restrict__ x, RowMap xm, const float* __restrict__ w,
                                                                  long long w_batch, float* __restrict__ y, RowMap ym, int M,
                                                                  int N, int K, int mtiles) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float4 xs4[kSkMT * kSkNnKS / 4];                      // [16][64 k], zero-padded (K may be any size: C + 365 logits)
   const int tid = threadIdx.x;
   const int z = blockIdx.z / mtiles, m0 = (blockIdx.z % mtiles) * kSkMT;
@@ -160,6 +164,8 @@ constexpr int kSkOutRows = 8;      // rows i of c per CTA
 __global__ void __launch_bounds__(256) skinny_outer_kernel(const float* __restrict__ a, RowMap am, const float* __restrict__ b, RowMap bm,
                                                            float* __restrict__ c, long long c_batch, float* __restrict__ colsum,
                                                            long long colsum_batch, int M, int I, int J, int accumulate) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float4 as4[kSkOutRows * kSkMT / 4];                   // [8 rows i][16 m]
   const int tid = threadIdx.x, z = blockIdx.z;
   const int i0 = blockIdx.y * kSkOutRows;
@@ -249,7 +255,7 @@ extern "C" int devias_skinny_nt(const float* x, const int64_t* x_map, const floa
   const int cols = threads >> 4;
   const dim3 grid((N + cols - 1) / cols, (M + kSkMT - 1) / kSkMT, batch);
   const size_t smem = (size_t)kSkMT * (K < kSkKC ? K : kSkKC) * 4;
-  skinny_nt_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(x, make_map(x_map), w, w_batch, bias, y, make_map(y_map), M, N, K);
+  DV_CHECK_CUDA(launch_k(skinny_nt_kernel, dim3(grid), dim3((unsigned)(threads)), (size_t)(smem), (cudaStream_t)stream, x, make_map(x_map), w, w_batch, bias, y, make_map(y_map), M, N, K));
   DV_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return DEVIAS_OK;
@@ -262,7 +268,7 @@ extern "C" int devias_skinny_nn(const float* x, const int64_t* x_map, const floa
   DV_REQUIRE(x_map && x_map[1] > 0 && y_map && y_map[1] > 0, "skinny_nn: row maps need inner > 0");
   const int mtiles = (M + kSkMT - 1) / kSkMT;
   const dim3 grid((N + kSkNnThreads - 1) / kSkNnThreads, (K + kSkNnKS - 1) / kSkNnKS, batch * mtiles);
-  skinny_nn_kernel<<<grid, kSkNnThreads, 0, (cudaStream_t)stream>>>(x, make_map(x_map), w, w_batch, y, make_map(y_map), M, N, K, mtiles);
+  DV_CHECK_CUDA(launch_k(skinny_nn_kernel, dim3(grid), dim3((unsigned)(kSkNnThreads)), (size_t)(0), (cudaStream_t)stream, x, make_map(x_map), w, w_batch, y, make_map(y_map), M, N, K, mtiles));
   DV_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return DEVIAS_OK;
@@ -278,8 +284,8 @@ extern "C" int devias_skinny_outer(const float* a, const int64_t* a_map, const f
   const int j4 = J / 4;
   const int threads = j4 >= 256 ? 256 : (j4 + 31) / 32 * 32;
   const dim3 grid((j4 + threads - 1) / threads, (I + kSkOutRows - 1) / kSkOutRows, batch);
-  skinny_outer_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(a, make_map(a_map), b, make_map(b_map), c, c_batch, colsum,
-                                                                 colsum_batch, M, I, J, accumulate);
+  DV_CHECK_CUDA(launch_k(skinny_outer_kernel, dim3(grid), dim3((unsigned)(threads)), (size_t)(0), (cudaStream_t)stream, a, make_map(a_map), b, make_map(b_map), c, c_batch, colsum,
+                                                                 colsum_batch, M, I, J, accumulate));
   DV_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return DEVIAS_OK;

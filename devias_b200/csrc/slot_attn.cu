@@ -65,6 +65,8 @@ __device__ __forceinline__ uint32_t tile_chunk(uint32_t tile, int tok, int c4) {
 template <int HS>
 __global__ void __launch_bounds__(kSlotThreads, 1)
 slot_stream_fwd_kernel(const __grid_constant__ CUtensorMap tmTok, const SlotParams p) {
+  pdl_trigger();
+  pdl_wait();
   using Cfg = SlotCfg<HS>;
   constexpr int S = HS / 4;
   extern __shared__ uint8_t smem_raw[];
@@ -282,6 +284,8 @@ struct SlotCfg2 {
 template <int HS>
 __global__ void __launch_bounds__(SlotCfg2<HS>::THREADS, 1)
 slot_stream_fwd2_kernel(const __grid_constant__ CUtensorMap tmTok, const SlotParams p) {
+  pdl_trigger();
+  pdl_wait();
   using Cfg = SlotCfg2<HS>;
   constexpr int S = HS / 4;
   constexpr int HE = Cfg::HE, WS = Cfg::WS, TPL = Cfg::TPL, NG = Cfg::NG, NE = Cfg::NE;
@@ -613,6 +617,8 @@ struct SlotBwdParams {
 template <int HS, int HEADS>
 __global__ void __launch_bounds__(kSlotThreads, 1)
 slot_stream_bwd_kernel(const __grid_constant__ CUtensorMap tmTok, const SlotBwdParams p) {
+  pdl_trigger();
+  pdl_wait();
   using Cfg = SlotBwdCfg<HS>;
   constexpr int S = HS / HEADS;
   const long long row0 = (long long)blockIdx.y * p.hs_total + p.hs_off;      // first (head, slot) row of this clip / launch
@@ -845,6 +851,8 @@ __device__ __forceinline__ uint64_t f2_dup(float w) { return f2_pack(w, w); }
 // coefficients are stored once (not as duplicated FFMA2 pairs) and each thread applies them to three channel pairs.
 __global__ void __launch_bounds__(SlotBwd2Cfg::THREADS, 1)
 slot_stream_bwd2_kernel(const __grid_constant__ CUtensorMap tmTok, const SlotBwdParams p) {
+  pdl_trigger();
+  pdl_wait();
   using Cfg = SlotBwd2Cfg;
   constexpr int HS = 8;
   extern __shared__ uint8_t smem_raw[];
@@ -1099,7 +1107,7 @@ static int launch_slot_bwd2(const CUtensorMap& tm, const SlotBwdParams& p, cudaS
   if (grid > (total + 1) / 2) grid = (total + 1) / 2;             // at least two tiles per CTA
   const double bytes = (double)p.B * p.N * kSD * 4 * (p.accumulate ? 3.0 : 2.0);
   const int prof = prof_begin(DEVIAS_PROF_SLOT, bytes, s);
-  slot_stream_bwd2_kernel<<<dim3((unsigned)grid), Cfg::THREADS, Cfg::BYTES, s>>>(tm, p);
+  DV_CHECK_CUDA(launch_k(slot_stream_bwd2_kernel, dim3((unsigned)grid), dim3((unsigned)(Cfg::THREADS)), (size_t)(Cfg::BYTES), s, tm, p));
   prof_end(prof, s);
   DV_CHECK_CUDA(cudaGetLastError());
   count_launch();
@@ -1118,7 +1126,7 @@ static int launch_slot_bwd(const CUtensorMap& tm, const SlotBwdParams& p, int sp
   }
   const double bytes = (double)p.B * p.N * kSD * 4 * (p.accumulate ? 3.0 : 2.0);
   const int prof = prof_begin(DEVIAS_PROF_SLOT, bytes, s);
-  kern<<<dim3(splits, p.B), kSlotThreads, Cfg::BYTES, s>>>(tm, p);
+  DV_CHECK_CUDA(launch_k(kern, dim3(splits, p.B), dim3((unsigned)(kSlotThreads)), (size_t)(Cfg::BYTES), s, tm, p));
   prof_end(prof, s);
   DV_CHECK_CUDA(cudaGetLastError());
   count_launch();
@@ -1151,7 +1159,7 @@ static int launch_slot_fwd(const CUtensorMap& tm, const SlotParams& p, int split
     long long grid = sm_count();
     if (grid > (total + 1) / 2) grid = (total + 1) / 2;
     const int prof = prof_begin(DEVIAS_PROF_SLOT, bytes, s);
-    slot_stream_fwd2_kernel<HS><<<dim3((unsigned)grid), Cfg::THREADS, Cfg::BYTES, s>>>(tm, p);
+    DV_CHECK_CUDA(launch_k(slot_stream_fwd2_kernel<HS>, dim3((unsigned)grid), dim3((unsigned)(Cfg::THREADS)), (size_t)(Cfg::BYTES), s, tm, p));
     prof_end(prof, s);
   } else {
     using Cfg = SlotCfg<HS>;
@@ -1161,7 +1169,7 @@ static int launch_slot_fwd(const CUtensorMap& tm, const SlotParams& p, int split
       attr_done = true;
     }
     const int prof = prof_begin(DEVIAS_PROF_SLOT, bytes, s);
-    slot_stream_fwd_kernel<HS><<<dim3(splits, p.B), kSlotThreads, Cfg::BYTES, s>>>(tm, p);
+    DV_CHECK_CUDA(launch_k(slot_stream_fwd_kernel<HS>, dim3(splits, p.B), dim3((unsigned)(kSlotThreads)), (size_t)(Cfg::BYTES), s, tm, p));
     prof_end(prof, s);
   }
   DV_CHECK_CUDA(cudaGetLastError());
@@ -1174,6 +1182,8 @@ static int launch_slot_fwd(const CUtensorMap& tm, const SlotParams& p, int split
 // the ceiling the TMA path itself gives the streaming kernels.  One thread issues, every warp touches each tile once.
 __global__ void __launch_bounds__(256, 1)
 slot_stream_probe_kernel(const __grid_constant__ CUtensorMap tmTok, int B, int tpc, int stages, float* out) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + stages * kSTileBytes);
@@ -1281,7 +1291,7 @@ extern "C" int devias_debug_token_stream(const float* tokens, int batch, int n_t
   long long grid = sm_count();
   const long long total = (long long)batch * tiles;
   if (grid > total) grid = total;
-  slot_stream_probe_kernel<<<dim3((unsigned)grid), 256, bytes, (cudaStream_t)stream>>>(tm, batch, tiles, stages, scratch);
+  DV_CHECK_CUDA(launch_k(slot_stream_probe_kernel, dim3((unsigned)grid), dim3((unsigned)(256)), (size_t)(bytes), (cudaStream_t)stream, tm, batch, tiles, stages, scratch));
   DV_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return DEVIAS_OK;

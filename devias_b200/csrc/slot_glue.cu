@@ -33,6 +33,8 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 __global__ void __launch_bounds__(kGT) slot_fold_fwd_kernel(const float* __restrict__ qt, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, float scale, float* __restrict__ g,
                                                             float* __restrict__ G, float* __restrict__ c0, int rows) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[kGT / 32];
   const int t = threadIdx.x;
   float gm[3], bt[3];
@@ -59,6 +61,8 @@ __global__ void __launch_bounds__(kGT) slot_fold_bwd_kernel(const float* __restr
                                                             const float* __restrict__ dG, const float* __restrict__ dc0,
                                                             float* __restrict__ dqt, float* __restrict__ dgamma,
                                                             float* __restrict__ dbeta, int rows) {
+  pdl_trigger();
+  pdl_wait();
   const int t = threadIdx.x;
   float gm[3], bt[3], ag[3] = {0.f, 0.f, 0.f}, ab[3] = {0.f, 0.f, 0.f};
 #pragma unroll
@@ -85,6 +89,8 @@ __global__ void __launch_bounds__(kGT) slot_fold_bwd_kernel(const float* __restr
 __global__ void __launch_bounds__(kGT) slot_ctx_fwd_kernel(const float* __restrict__ U, const float* __restrict__ m,
                                                            const float* __restrict__ A, const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, float eps, float* __restrict__ cbar, int rows) {
+  pdl_trigger();
+  pdl_wait();
   const int t = threadIdx.x;
   float gm[3], bt[3];
 #pragma unroll
@@ -105,6 +111,8 @@ __global__ void __launch_bounds__(kGT) slot_ctx_bwd_kernel(const float* __restri
                                                            const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                                            float* __restrict__ dU, float* __restrict__ dm, float* __restrict__ dA,
                                                            float* __restrict__ dgamma, float* __restrict__ dbeta, int rows) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[kGT / 32];
   const int t = threadIdx.x;
   float gm[3], bt[3], ag[3] = {0.f, 0.f, 0.f}, ab[3] = {0.f, 0.f, 0.f};
@@ -152,7 +160,7 @@ extern "C" int devias_slot_fold_fwd(const float* qt, const float* gamma, const f
                                     int rows, int dim, void* stream) {
   DV_REQUIRE(qt && gamma && beta && g && G && c0, "null pointer");
   DV_REQUIRE(dim == kGD && rows > 0, "dim must be 768");
-  slot_fold_fwd_kernel<<<glue_grid(rows), kGT, 0, (cudaStream_t)stream>>>(qt, gamma, beta, scale, g, G, c0, rows);
+  DV_CHECK_CUDA(launch_k(slot_fold_fwd_kernel, dim3((unsigned)(glue_grid(rows))), dim3((unsigned)(kGT)), (size_t)(0), (cudaStream_t)stream, qt, gamma, beta, scale, g, G, c0, rows));
   DV_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return DEVIAS_OK;
@@ -163,7 +171,7 @@ extern "C" int devias_slot_fold_bwd(const float* qt, const float* gamma, const f
                                     void* stream) {
   DV_REQUIRE(qt && gamma && beta && dg && dG && dc0 && dqt && dgamma && dbeta, "null pointer");
   DV_REQUIRE(dim == kGD && rows > 0, "dim must be 768");
-  slot_fold_bwd_kernel<<<glue_grid(rows), kGT, 0, (cudaStream_t)stream>>>(qt, gamma, beta, scale, dg, dG, dc0, dqt, dgamma, dbeta, rows);
+  DV_CHECK_CUDA(launch_k(slot_fold_bwd_kernel, dim3((unsigned)(glue_grid(rows))), dim3((unsigned)(kGT)), (size_t)(0), (cudaStream_t)stream, qt, gamma, beta, scale, dg, dG, dc0, dqt, dgamma, dbeta, rows));
   DV_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return DEVIAS_OK;
@@ -173,7 +181,7 @@ extern "C" int devias_slot_ctx_fwd(const float* U, const float* m, const float* 
                                    float* cbar, int rows, int dim, void* stream) {
   DV_REQUIRE(U && m && A && gamma && beta && cbar, "null pointer");
   DV_REQUIRE(dim == kGD && rows > 0, "dim must be 768");
-  slot_ctx_fwd_kernel<<<glue_grid(rows), kGT, 0, (cudaStream_t)stream>>>(U, m, A, gamma, beta, eps, cbar, rows);
+  DV_CHECK_CUDA(launch_k(slot_ctx_fwd_kernel, dim3((unsigned)(glue_grid(rows))), dim3((unsigned)(kGT)), (size_t)(0), (cudaStream_t)stream, U, m, A, gamma, beta, eps, cbar, rows));
   DV_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return DEVIAS_OK;
@@ -184,7 +192,7 @@ extern "C" int devias_slot_ctx_bwd(const float* dcbar, const float* U, const flo
                                    int dim, void* stream) {
   DV_REQUIRE(dcbar && U && m && A && gamma && beta && dU && dm && dA && dgamma && dbeta, "null pointer");
   DV_REQUIRE(dim == kGD && rows > 0, "dim must be 768");
-  slot_ctx_bwd_kernel<<<glue_grid(rows), kGT, 0, (cudaStream_t)stream>>>(dcbar, U, m, A, gamma, beta, eps, dU, dm, dA, dgamma, dbeta, rows);
+  DV_CHECK_CUDA(launch_k(slot_ctx_bwd_kernel, dim3((unsigned)(glue_grid(rows))), dim3((unsigned)(kGT)), (size_t)(0), (cudaStream_t)stream, dcbar, U, m, A, gamma, beta, eps, dU, dm, dA, dgamma, dbeta, rows));
   DV_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return DEVIAS_OK;

@@ -177,14 +177,15 @@ class LayerNormFn(torch.autograd.Function):
 # --------------------------------------------------------------------------------------------
 def _attention_fwd(qkv, B, N, H, need_grad):
     """Softmax attention over the packed qkv [B*N, 3*H*hd] bf16 (q scaled by hd^-0.5 BEFORE q.k^T,
-    model/modeling_slot.py:105-112).  Returns (out [B*N, H*hd] bf16, state for backward)."""
-    from . import attention
-    return attention.attention_fwd(qkv, B, N, H, need_grad)
+    model/modeling_slot.py:105-112) on the tcgen05 flash kernels (csrc/flash_attn.cu).
+    Returns (out [B*N, H*hd] bf16, state for backward)."""
+    out, lse2 = ops.flash_attn_fwd(qkv, B, N, H, need_lse=need_grad)
+    return out, ((qkv, out, lse2, B, N, H) if need_grad else None)
 
 
-def _attention_bwd(state, dout, delta=None):
-    from . import attention
-    return attention.attention_bwd(state, dout, delta)
+def _attention_bwd(state, dout):
+    qkv, out, lse2, B, N, H = state
+    return ops.flash_attn_bwd(qkv, out, dout.contiguous(), lse2, B, N, H)
 
 
 class EncoderBlockFn(torch.autograd.Function):
@@ -255,8 +256,6 @@ class EncoderBlockFn(torch.autograd.Function):
         dx1, dyb = ops.layernorm_bwd(dx1n, x1, mean2, rstd2, n2w, d_resid=dx2.view(M, D), dgamma=dn2w, dbeta=dn2b,
                                       dx_colsum=dproj_b, inplace=ours, row_scale=s1, rows_per_scale=N)
         # ---- attention branch: x1 = x + s1 * (attn(xn) Wp^T + bp)
-        # (ops.gemm_dgrad_delta can produce the flash backward's row term in this GEMM's epilogue; measured slower than the
-        #  stand-alone 15 us kernel because this K = 768 GEMM is epilogue-bound: 14.40 vs 14.26 ms per step)
         dattn = ops.gemm(dyb, proj16, ops.EPI_STORE_BF16, b_mn=True)                     # [M, D]
         ops.gemm(dyb, attn_out, ops.EPI_ATOMIC_F32, a_mn=True, b_mn=True, out=dproj_w, split_k=_wgrad_split(D, D, M))
         dqkv = _attention_bwd(ctx.attn_state, dattn)                                     # [M, 3D] bf16

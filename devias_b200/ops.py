@@ -237,37 +237,16 @@ def flash_attn_fwd(qkv: torch.Tensor, B: int, N: int, H: int, need_lse=True):
     return out, lse2
 
 
-def gemm_dgrad_delta(dy: torch.Tensor, w: torch.Tensor, o_fwd: torch.Tensor, B: int, N: int, H: int):
-    """dout = dy @ w (w [n_out_of_forward = K, n] i.e. the forward weight [D, D] read mn-major) and, from the same epilogue, the
-    flash-attention backward row term delta [B*H*Npad] = sum_d dout * o_fwd.  -> (dout bf16 [B*N, H*64], delta fp32)"""
-    _need_cuda(dy, w, o_fwd)
-    assert dy.dtype == w.dtype == o_fwd.dtype == torch.bfloat16 and dy.dim() == 2 and dy.stride(1) == 1 and w.stride(1) == 1
-    M, K = dy.shape
-    n = w.shape[1]
-    assert w.shape[0] == K and n == H * 64 and M == B * N and o_fwd.shape == (M, n) and o_fwd.stride(1) == 1
-    npad = (N + 127) // 128 * 128
-    dout = torch.empty(M, n, device=dy.device, dtype=torch.bfloat16)
-    delta = torch.zeros(B * H * npad, device=dy.device, dtype=torch.float32)    # rows q >= N stay 0
-    rc = _lib.lib().devias_gemm_dgrad_delta(dy.data_ptr(), dy.stride(0), w.data_ptr(), w.stride(0), 1, M, n, K, dout.data_ptr(),
-                                            dout.stride(0), o_fwd.data_ptr(), o_fwd.stride(0), delta.data_ptr(), N, npad, H,
-                                            _stream())
-    _lib.check(rc, 'gemm_dgrad_delta')
-    return dout, delta
-
-
-def flash_attn_bwd(qkv, out, dout, lse2, B: int, N: int, H: int, delta=None):
-    """-> dqkv bf16 [B*N, 3*H*64]; `delta` (from gemm_dgrad_delta) skips the row-term kernel"""
+def flash_attn_bwd(qkv, out, dout, lse2, B: int, N: int, H: int):
+    """-> dqkv bf16 [B*N, 3*H*64]  (include/devias_b200.h: devias_flash_attn_bwd)"""
     _need_cuda(qkv, out, dout, lse2)
     assert dout.dtype == torch.bfloat16 and dout.is_contiguous() and out.is_contiguous() and qkv.is_contiguous()
     npad = (N + 127) // 128 * 128
     dqkv = torch.empty_like(qkv)
-    ready = delta is not None
-    if not ready:
-        delta = torch.empty(B * H * npad, device=qkv.device, dtype=torch.float32)
-    assert delta.numel() == B * H * npad and delta.dtype == torch.float32
+    aug = torch.empty(B * H * npad * 16, device=qkv.device, dtype=torch.bfloat16)     # [lse | delta] k-step operand blocks
     dq = torch.empty(B * N * H * 64, device=qkv.device, dtype=torch.float32)
     rc = _lib.lib().devias_flash_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse2.data_ptr(), dqkv.data_ptr(),
-                                          delta.data_ptr(), dq.data_ptr(), B, N, H, 64, 0.125, int(ready), _stream())
+                                          aug.data_ptr(), dq.data_ptr(), B, N, H, 64, 0.125, _stream())
     _lib.check(rc, 'flash_attn_bwd')
     return dqkv
 

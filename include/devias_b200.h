@@ -68,7 +68,6 @@ int devias_profile_end(int kind, double* total_ms, double* total_work, int64_t* 
 #define DEVIAS_EPI_DGELU_BF16 3
 #define DEVIAS_EPI_RESID_F32 4
 #define DEVIAS_EPI_ATOMIC_F32 5
-#define DEVIAS_EPI_DELTA_BF16 6 /* internal to devias_gemm_dgrad_delta */
 int devias_gemm_bf16(const void* a, int64_t lda, int a_mn_major, const void* b, int64_t ldb, int b_mn_major, int m, int n,
                      int k, int epilogue, void* out, int64_t ldo, void* out2, int64_t ldo2, const float* bias,
                      const void* aux, int64_t ldaux, int aux_row_mod, const float* row_scale, int rows_per_scale,
@@ -80,21 +79,13 @@ int devias_gemm_bf16(const void* a, int64_t lda, int a_mn_major, const void* b, 
  * model/modeling_slot.py:102-112 (q*scale, q@k^T, softmax, attn@v, transpose/reshape) without materialising the
  * [12, seq, seq] probabilities.  lse2: fp32 [batch, heads, seq_pad] (seq_pad = seq rounded up to 128), log2-domain
  * log-sum-exp kept for the backward (may be NULL for inference).
- * Backward: dqkv bf16 [batch*seq, 3*heads*64] from dout; delta_ws fp32 [batch*heads*seq_pad] and dq_ws fp32
- * [batch*seq*heads*64] are caller-provided scratch buffers (dq_ws is zeroed by the call). */
+ * Backward: dqkv bf16 [batch*seq, 3*heads*64] from dout.  Caller-provided scratch: aug_ws bf16 [batch*heads*seq_pad*16]
+ * (the log-sum-exp / row-term operand blocks the kernel's extra MMA k-step reads) and dq_ws fp32 [batch*seq*heads*64]
+ * (zeroed by the call, accumulated with red.global.add, converted into dqkv at the end). */
 int devias_flash_attn_fwd(const void* qkv, void* out, float* lse2, int batch, int seq, int heads, int head_dim, float scale,
                           void* stream);
-int devias_flash_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse2, void* dqkv, float* delta_ws,
-                          float* dq_ws, int batch, int seq, int heads, int head_dim, float scale, int delta_ready, void* stream);
-/* delta_ready != 0: delta_ws already holds delta[b, h, q] = sum_d dout * out (rows q >= seq finite), e.g. from
- * devias_gemm_dgrad_delta below, and is not recomputed.
- *
- * dout = dy w (input gradient of Attention.proj, model/modeling_slot.py:113; w [n, k] row-major read mn-major, or [k, n] with
- * w_mn_major = 0) with delta produced in the same epilogue: n = heads * 64, m = batch * seq rows, o_fwd = the forward
- * attention output [m, n] bf16, delta fp32 [batch * heads * npad]. */
-int devias_gemm_dgrad_delta(const void* dy, int64_t ld_dy, const void* w, int64_t ldw, int w_mn_major, int m, int n, int k,
-                            void* dout, int64_t ld_dout, const void* o_fwd, int64_t ld_o, float* delta, int seq, int npad,
-                            int heads, void* stream);
+int devias_flash_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse2, void* dqkv, void* aug_ws,
+                          float* dq_ws, int batch, int seq, int heads, int head_dim, float scale, void* stream);
 
 /* ---- streaming slot attention (folded form; devias_b200/slot_attention.py) ----------------------------
  * One pass over the context tokens of every clip, replacing per layer: LayerNorm(context) + to_k + to_v + q k^T + slot-axis
