@@ -258,7 +258,7 @@ def measure_train(name, cfg, args, dev, world, rank, with_roofline=True, with_e2
             dist.barrier()
         torch.cuda.synchronize()
 
-    cuts = [int(c) for c in args.cuts.split(',') if c]
+    cuts = [int(c) for c in args.cuts.split(',') if c.strip().isdigit()]
     # ---------------------------------------------------------------- warm-up (+ graph capture of the whole step)
     use_graph = not args.no_graph
     for i in range(max(args.warmup, 3) if not use_graph else 1):

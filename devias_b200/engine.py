@@ -128,6 +128,8 @@ class GraphedTrainStep:
         if self.split:
             if cuts is None:
                 cuts = [split_block]
+            # cuts = []: one backward piece and ONE all-reduce of the whole arena after it (nothing overlaps the backward: the
+            # collective then has every SM and NVLink to itself instead of taking SMs away from the persistent compute kernels)
             cuts = sorted({max(1, min(int(c), len(blocks) - 1)) for c in cuts}, reverse=True)
             self.cuts = cuts
             # parameter sets per backward piece: piece 0 = everything above the first cut, ..., last = below the last cut
@@ -242,7 +244,7 @@ class GraphedTrainStep:
                 loss, _, _ = train_class_batch(self.model, self.scene_model, b['clip'], b['target'], self.crit, (b['fg'], b['fgf']),
                                                teacher_logits=b.get('teacher'))
                 root = loss / self.update_freq if self.update_freq != 1 else loss
-                if self.split:
+                if self.split and self.cuts:
                     torch.autograd.backward([root], inputs=self.piece_params[0] + [self._taps[self.cuts[0]][1]], retain_graph=True)
                 else:
                     root.backward()
