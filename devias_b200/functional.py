@@ -116,11 +116,21 @@ class PatchEmbedFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, clip, weight, bias, w16, pos_table):
         B = clip.shape[0]
-        patches = ops.patchify(clip)                      # [B*N, 1536] bf16
-        N = patches.shape[0] // B
         D = weight.shape[0]
-        x0 = ops.gemm(patches, w16.view(D, -1), ops.EPI_RESID_F32, bias=bias, aux=pos_table, aux_row_mod=N)
-        ctx.save_for_backward(patches)
+        implicit = (clip.dtype == torch.float32 and tuple(clip.shape[1:]) == (3, 16, 224, 224) and D == 768
+                    and pos_table.dtype == torch.float32 and tuple(pos_table.shape) == (1568, 768))
+        if implicit:
+            # implicit GEMM: the clip is the A operand (5-D TMA boxes, tf32 MMAs); nothing is materialised or saved but the clip
+            clip = clip.contiguous()
+            x0 = ops.patch_embed_fwd(clip, weight.detach().contiguous(), bias.detach(), pos_table.contiguous())
+            N = x0.shape[0] // B
+            ctx.save_for_backward(clip)
+        else:
+            patches = ops.patchify(clip)                      # [B*N, 1536] bf16
+            N = patches.shape[0] // B
+            x0 = ops.gemm(patches, w16.view(D, -1), ops.EPI_RESID_F32, bias=bias, aux=pos_table, aux_row_mod=N)
+            ctx.save_for_backward(patches)
+        ctx.implicit = implicit
         ctx.wshape = weight.shape
         ctx.sinks = grad_sinks(weight, bias)
         return x0.view(B, N, D)
@@ -128,6 +138,8 @@ class PatchEmbedFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dx0):
         (patches,) = ctx.saved_tensors
+        if ctx.implicit:
+            patches = ops.patchify(patches)                   # the saved tensor is the clip: tube rows for the weight-gradient GEMM
         D = ctx.wshape[0]
         dyb = _take_bf16(dx0).view(-1, D)
         direct = ctx.sinks is not None

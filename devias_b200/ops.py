@@ -152,6 +152,20 @@ def patchify(clip: torch.Tensor):
     return out
 
 
+def patch_embed_fwd(clip: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, pos: torch.Tensor):
+    """clip fp32 [B,3,16,224,224], weight fp32 [768,3,2,16,16], bias [768], pos fp32 [1568,768] -> fp32 [B*1568, 768]
+    (include/devias_b200.h: devias_patch_embed_fwd -- implicit GEMM, the clip is read in place by TMA)"""
+    _need_cuda(clip, weight, bias, pos)
+    assert clip.dtype == weight.dtype == pos.dtype == torch.float32 and clip.is_contiguous() and weight.is_contiguous() and pos.is_contiguous()
+    B, C, T, H, W = clip.shape
+    D = weight.shape[0]
+    out = torch.empty(B * (T // 2) * (H // 16) * (W // 16), D, device=clip.device, dtype=torch.float32)
+    rc = _lib.lib().devias_patch_embed_fwd(clip.data_ptr(), weight.data_ptr(), bias.data_ptr(), pos.data_ptr(), out.data_ptr(),
+                                           B, C, T, H, W, D, _stream())
+    _lib.check(rc, 'patch_embed_fwd')
+    return out
+
+
 def _rowmap(outer, inner, ld, batch):
     import ctypes
     return (ctypes.c_int64 * 4)(int(outer), int(inner), int(ld), int(batch))

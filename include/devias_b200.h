@@ -135,6 +135,12 @@ int devias_colsum_bf16(const void* a, int64_t lda, int rows, int cols, float* ou
  * Conv3d(k=s=(2,16,16)) (model/modeling_slot.py:167-176) becomes devias_gemm_bf16 with the RESID_F32 epilogue adding the
  * bias and the sin-cos table (:354-355).  row = t*196 + h*14 + w, col = c*512 + dt*256 + dy*16 + dx. */
 int devias_cast_f32_bf16(const float* in, void* out, int64_t n, void* stream);
+/* Tube patch embedding as an implicit GEMM (model/modeling_slot.py:167-177 Conv3d(k = s = (2,16,16)) + flatten/transpose, bias, and
+ * the position table of :354-355 in the epilogue): out fp32 [B*1568, 768] = im2col(clip) W^T + bias + pos[token % 1568].
+ * The A operand is fetched by a 5-D TMA box straight from the NCTHW fp32 clip [B, 3, 16, 224, 224] (no patch matrix, no
+ * conversion pass; kind::tf32 MMAs on the fp32 data); weight = the fp32 Conv3d weight [768, 3*2*16*16]; pos fp32 [1568, 768]. */
+int devias_patch_embed_fwd(const float* clip, const float* weight, const float* bias, const float* pos, float* out, int batch,
+                           int chans, int frames, int height, int width, int dim, void* stream);
 /* out_bf16[r,:] = bf16(in_f32[r,:] * row_scale[r / rows_per_scale]) -- gradient entering a drop-path branch (modeling_slot.py:36-47) */
 int devias_scale_rows_cast(const float* in, void* out, int rows, int cols, const float* row_scale, int rows_per_scale,
                            void* stream);

@@ -82,3 +82,19 @@ def test_patch_embed_matches_oracle():
     x0 = ops.gemm(ops.patchify(clip.cuda()), w16, ops.EPI_RESID_F32, bias=sd['patch_embed.proj.bias'].cuda(),
                   aux=O.sinusoid_table(1568, 768)[0].cuda().contiguous(), aux_row_mod=1568)
     assert_close(x0.cpu().view(2, 1568, 768), ref, 4e-3, 'patch embed + pos')
+
+
+@pytest.mark.parametrize('B', [1, 3])
+def test_patch_embed_implicit_gemm_vs_conv3d(B):
+    """the implicit-GEMM tube patch embedding (5-D TMA boxes over the NCTHW clip, tf32 MMAs) against the Conv3d of
+    model/modeling_slot.py:167-177 + flatten/transpose + bias + position table, evaluated in float64"""
+    from devias_b200 import ops
+    clip = O.synth_clips(B, seed=21).cuda()
+    w = _r((768, 3, 2, 16, 16), 6, 1.0 / 39.0)
+    bias = _r((768,), 7, 0.02)
+    pos = O.sinusoid_table(1568, 768)[0].cuda().contiguous()
+    out = ops.patch_embed_fwd(clip, w, bias, pos)
+    ref = F.conv3d(clip.double(), w.double(), bias.double(), stride=(2, 16, 16)).flatten(2).transpose(1, 2) + pos.double()
+    assert out.shape == (B * 1568, 768)
+    # tf32 operands (10-bit mantissa), fp32 accumulation over k = 1536
+    assert_close(out.view(B, 1568, 768), ref, 1.5e-3, 'implicit patch embed')
