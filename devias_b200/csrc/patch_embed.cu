@@ -12,6 +12,11 @@
 // of the encoder), fp32 accumulation in tensor memory.  k = c*512 + dt*256 + dy*16 + dx is also the memory order of the Conv3d
 // weight [768, 3, 2, 16, 16], so B is a plain 2-D box of the fp32 master weight.
 //
+// The WEIGHT GRADIENT keeps the explicit route (devias_patchify in the backward + the bf16 MN-major GEMM): its contraction runs
+// over tokens, which forces MN-major operands, and tcgen05 kind::tf32 accepts K-major operands only (an MN-major tf32 prototype
+// of dW = dX0^T im2col(clip) over the same 5-D boxes returned exact zeros on sm_100a; the 16-bit kinds transpose, the 32-bit one
+// does not) -- an in-kernel fp32 -> bf16 conversion stage would be needed to drop the patch matrix there too.
+//
 //   CTA  = (98-token tile, 256-column block of the 768 outputs); 96 k-chunks of 16 through a 6-stage TMA ring
 //   warp 0 : TMA producer      warp 1 : tcgen05.mma issuer (M = 128 rows of which 98 are tokens, N = 256, K = 8 per instruction,
 //                              two per chunk)
