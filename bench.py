@@ -54,6 +54,7 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--cuts', default='8,4,1', help='data-parallel step: encoder blocks at which the backward graph is cut')
+    ap.add_argument('--grad-exchange', default='bf16', choices=['fp32', 'bf16'], help='data-parallel gradient all-reduce precision')
     ap.add_argument('--no-secondary', action='store_true', help='skip the UCF-101 B=8 secondary line')
     ap.add_argument('--no-extras', action='store_true', help='skip slot grid / eval sweep / gpu reference (N=1 extras)')
     ap.add_argument('--torch-adamw', action='store_true', help='torch fused AdamW instead of the arena optimizer pass')
@@ -266,7 +267,7 @@ def measure_train(name, cfg, args, dev, world, rank, with_roofline=True, with_e2
     barrier()
     graphed = None
     if use_graph:
-        graphed = engine.GraphedTrainStep(model, crit, opt, devb, reducer=reducer, warmup=1, cuts=cuts)
+        graphed = engine.GraphedTrainStep(model, crit, opt, devb, reducer=reducer, warmup=1, cuts=cuts, grad_exchange=args.grad_exchange)
         for i in range(max(args.warmup, 3)):
             graphed(i % nbuf)
         barrier()
@@ -332,7 +333,7 @@ def measure_train(name, cfg, args, dev, world, rank, with_roofline=True, with_e2
     prof = None
     if with_roofline and use_graph:
         _lib.profile_begin(capture_only=True)
-        pstep = engine.GraphedTrainStep(model, crit, opt, [devb[0]], reducer=reducer, warmup=0, cuts=cuts)
+        pstep = engine.GraphedTrainStep(model, crit, opt, [devb[0]], reducer=reducer, warmup=0, cuts=cuts, grad_exchange=args.grad_exchange)
         _lib.profile_pause()
         pstep(0)
         barrier()
@@ -609,7 +610,7 @@ def main():
         C, B = primary['C'], primary['B']
         mode = ('eager' if not primary['graphed'] else 'cuda-graph replay: fwd+loss+bwd graph + update graph' if world == 1 else
                 f'cuda graphs per step: backward cut at encoder blocks {primary["cuts"]}; the NCCL all-reduce of each finished gradient '
-                f'range (flat fp32 arena) overlaps the next backward piece; update graph last')
+                f'range (flat arena, exchanged as {args.grad_exchange}) overlaps the next backward piece; update graph last')
         out = {
             'metric': METRIC, 'value': out_p['value'], 'unit': 'clips/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': max(args.warmup, 3), 'ms_per_step': out_p['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak',

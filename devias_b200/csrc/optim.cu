@@ -42,7 +42,8 @@ __global__ void __launch_bounds__(256) adamw_arena_kernel(float* __restrict__ p,
                                                           float* __restrict__ v, __nv_bfloat16* __restrict__ p16,
                                                           const int* __restrict__ seg_start, const int* __restrict__ seg_group,
                                                           int n_seg, const float* __restrict__ hyper,
-                                                          const float* __restrict__ sumsq, long long n8, int zero_grad) {
+                                                          const float* __restrict__ sumsq, long long n8, int zero_grad,
+                                                          const __nv_bfloat16* __restrict__ g16) {
   pdl_trigger();
   pdl_wait();
   __shared__ int s_start[MAX_SEGS + 1];
@@ -76,7 +77,15 @@ __global__ void __launch_bounds__(256) adamw_arena_kernel(float* __restrict__ p,
     float pp[8], gg[8], mm[8], vv[8];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      const float4 a = reinterpret_cast<const float4*>(p)[2 * i + h], b = __ldcs(reinterpret_cast<const float4*>(g) + 2 * i + h);
+      const float4 a = reinterpret_cast<const float4*>(p)[2 * i + h];
+      float4 b;
+      if (g16 != nullptr) {       // gradients exchanged in bf16 (data parallel): the reduced values live in the bf16 buffer
+        const uint2 q = __ldcs(reinterpret_cast<const uint2*>(g16) + 2 * i + h);
+        const float2 lo = unpack_bf16(q.x), hi = unpack_bf16(q.y);
+        b = make_float4(lo.x, lo.y, hi.x, hi.y);
+      } else {
+        b = __ldcs(reinterpret_cast<const float4*>(g) + 2 * i + h);
+      }
       const float4 c = __ldcs(reinterpret_cast<const float4*>(m) + 2 * i + h), d = __ldcs(reinterpret_cast<const float4*>(v) + 2 * i + h);
       pp[4 * h] = a.x; pp[4 * h + 1] = a.y; pp[4 * h + 2] = a.z; pp[4 * h + 3] = a.w;
       gg[4 * h] = b.x; gg[4 * h + 1] = b.y; gg[4 * h + 2] = b.z; gg[4 * h + 3] = b.w;
@@ -124,7 +133,7 @@ extern "C" int devias_sumsq_f32(const float* x, int64_t n, float* out, void* str
 
 extern "C" int devias_adamw_arena(float* param, float* grad, float* exp_avg, float* exp_avg_sq, void* param_bf16,
                                   const int32_t* seg_start, const int32_t* seg_group, int n_seg, const float* hyper,
-                                  const float* grad_sumsq, int64_t n, int zero_grad, void* stream) {
+                                  const float* grad_sumsq, int64_t n, int zero_grad, const void* grad_bf16, void* stream) {
   using namespace dv;
   DV_REQUIRE(param && grad && exp_avg && exp_avg_sq && seg_start && seg_group && hyper, "null pointer");
   DV_REQUIRE(n % 8 == 0, "arena length must be a multiple of 8 elements");
@@ -137,7 +146,7 @@ extern "C" int devias_adamw_arena(float* param, float* grad, float* exp_avg, flo
   if (blocks > sm_count() * 8) blocks = sm_count() * 8;
   DV_CHECK_CUDA(launch_k(adamw_arena_kernel, dim3((unsigned)((int)blocks)), dim3((unsigned)(256)), (size_t)(0), static_cast<cudaStream_t>(stream), 
       param, grad, exp_avg, exp_avg_sq, static_cast<__nv_bfloat16*>(param_bf16), seg_start, seg_group, n_seg, hyper, grad_sumsq,
-      n8, zero_grad));
+      n8, zero_grad, static_cast<const __nv_bfloat16*>(grad_bf16)));
   DV_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return DEVIAS_OK;

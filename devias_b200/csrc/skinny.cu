@@ -228,6 +228,163 @@ __global__ void __launch_bounds__(256) skinny_outer_kernel(const float* __restri
   }
 }
 
+// ------------------------------------------------------------------------------------------------------- many rows (M > 32)
+// K400 training has 64 slot rows per GPU, an evaluation batch of 256 has 512: there the products stop being weight-read bound
+// and the row-tile-at-a-time kernels above re-read the weights per 16 rows.  Classic register-tiled fp32 SIMT GEMM instead:
+// CTA tile 64 x 64, 256 threads x (4 x 4) outputs, k-chunks of 16 staged in shared memory as [l][i] / [l][j] so that the inner
+// loop is 16 FMAs per two 16-byte shared loads; split over the contraction (atomics) where the output has too few tiles.
+//   MODE 0 (nt)   : C[i, j] = sum_l x[i, l] w[j, l]        i = row m (mapped), j = n          both operands contiguous along l
+//   MODE 1 (nn)   : C[i, j] += sum_l x[i, l] w[l, j]                                        B contiguous along j
+//   MODE 2 (outer): C[i, j] (+)= sum_l a[l, i] b[l, j]     l = row m (mapped)               both operands contiguous along i / j
+constexpr int kTg = 64, kTgK = 16, kTgPad = 4;
+
+struct TileArgs {
+  const float* A; const float* B; float* C;
+  RowMap am, bm, cm;                 // row maps of the row-mapped operands / output (unused ones are ignored)
+  long long a_batch, b_batch, c_batch;
+  int I, J, L;                       // output rows, output columns, contraction length
+  int ldb, ldc;                      // MODE 0: w row stride (= K); MODE 1: w row stride (= N); MODE 2: c row stride (= J)
+  int l_per_split;
+  int accumulate;                    // MODE 2: c += ; (MODE 0 / 1 always add atomically onto a pre-filled output)
+  float* colsum; long long colsum_batch;   // MODE 2: colsum[i] (+)= sum_l a[l, i]
+};
+
+__device__ __forceinline__ float4 ld4_guard(const float* p, int valid, bool vec) {
+  if (vec && valid >= 4) return __ldg(reinterpret_cast<const float4*>(p));
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (valid > 0) v.x = __ldg(p);
+  if (valid > 1) v.y = __ldg(p + 1);
+  if (valid > 2) v.z = __ldg(p + 2);
+  if (valid > 3) v.w = __ldg(p + 3);
+  return v;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) tile_gemm_kernel(const TileArgs p, int splits) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ float As[kTgK][kTg + kTgPad];
+  __shared__ float Bs[kTgK][kTg + kTgPad];
+  const int tid = threadIdx.x;
+  const int z = blockIdx.z / splits, split = blockIdx.z % splits;
+  const int i0 = blockIdx.y * kTg, j0 = blockIdx.x * kTg;
+  const int l_begin = split * p.l_per_split, l_end = min(p.L, l_begin + p.l_per_split);
+  const int ti = tid >> 4, tj = tid & 15;            // 16 x 16 threads, each 4 x 4 outputs
+  float acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+
+  // loader roles
+  //  "along l": thread -> (row r = tid / 4 of the 64, l4 = (tid % 4) * 4): one 16-byte load, stored transposed
+  //  "along i/j": thread -> (l = tid / 16, c4 = (tid % 16) * 4): one 16-byte load, stored as is
+  const int lr = tid >> 2, ll4 = (tid & 3) * 4;
+  const int sl = tid >> 4, sc4 = (tid & 15) * 4;
+  const float* a_row = nullptr; const float* b_row = nullptr;
+  bool a_vec = false, b_vec = false;
+  if (MODE == 0 || MODE == 1) {
+    const bool ok = i0 + lr < p.I;
+    a_row = ok ? p.A + p.am.off(i0 + lr, z) : nullptr;
+    a_vec = ok && ((reinterpret_cast<uintptr_t>(a_row) & 15) == 0);
+  }
+  if (MODE == 0) {
+    const bool ok = j0 + lr < p.J;
+    b_row = ok ? p.B + (long long)z * p.b_batch + (long long)(j0 + lr) * p.ldb : nullptr;
+    b_vec = ok && ((reinterpret_cast<uintptr_t>(b_row) & 15) == 0);
+  }
+  float csum = 0.f;                                   // MODE 2: column sums of a (thread tid < 64 <-> i = i0 + tid)
+  for (int l0 = l_begin; l0 < l_end; l0 += kTgK) {
+    float4 av = make_float4(0.f, 0.f, 0.f, 0.f), bv = av;
+    if (MODE == 0 || MODE == 1) {
+      if (a_row != nullptr) av = ld4_guard(a_row + l0 + ll4, l_end - (l0 + ll4), a_vec && ((l0 + ll4) & 3) == 0);
+    } else {
+      const int l = l0 + sl;
+      if (l < l_end) {
+        const float* src = p.A + p.am.off(l, z) + i0 + sc4;
+        av = ld4_guard(src, p.I - (i0 + sc4), (reinterpret_cast<uintptr_t>(src) & 15) == 0);
+      }
+    }
+    if (MODE == 0) {
+      if (b_row != nullptr) bv = ld4_guard(b_row + l0 + ll4, l_end - (l0 + ll4), b_vec && ((l0 + ll4) & 3) == 0);
+    } else {
+      const int l = l0 + sl;
+      if (l < l_end) {
+        const float* src = (MODE == 1 ? p.B + (long long)z * p.b_batch + (long long)l * p.ldb : p.B + p.bm.off(l, z)) + j0 + sc4;
+        bv = ld4_guard(src, p.J - (j0 + sc4), (reinterpret_cast<uintptr_t>(src) & 15) == 0);
+      }
+    }
+    __syncthreads();                                  // the previous chunk has been consumed
+    if (MODE == 0 || MODE == 1) {
+      As[ll4][lr] = av.x; As[ll4 + 1][lr] = av.y; As[ll4 + 2][lr] = av.z; As[ll4 + 3][lr] = av.w;
+    } else {
+      *reinterpret_cast<float4*>(&As[sl][sc4]) = av;
+    }
+    if (MODE == 0) {
+      Bs[ll4][lr] = bv.x; Bs[ll4 + 1][lr] = bv.y; Bs[ll4 + 2][lr] = bv.z; Bs[ll4 + 3][lr] = bv.w;
+    } else {
+      *reinterpret_cast<float4*>(&Bs[sl][sc4]) = bv;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int l = 0; l < kTgK; ++l) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[l][ti * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[l][tj * 4]);
+      const float aa[4] = {a4.x, a4.y, a4.z, a4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(aa[a], bb[b], acc[a][b]);
+    }
+    if (MODE == 2 && p.colsum != nullptr && blockIdx.x == 0 && tid < kTg) {
+#pragma unroll
+      for (int l = 0; l < kTgK; ++l) csum += As[l][tid];
+    }
+  }
+  // ---- output
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int i = i0 + ti * 4 + a;
+    if (i >= p.I) continue;
+    float* crow = (MODE == 2) ? p.C + (long long)z * p.c_batch + (long long)i * p.ldc : p.C + p.cm.off(i, z);
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int j = j0 + tj * 4 + b;
+      if (j >= p.J) continue;
+      if (MODE == 2) crow[j] = p.accumulate ? crow[j] + acc[a][b] : acc[a][b];
+      else atomicAdd(crow + j, acc[a][b]);
+    }
+  }
+  if (MODE == 2 && p.colsum != nullptr && blockIdx.x == 0 && tid < kTg && i0 + tid < p.I) {
+    float* d = p.colsum + (long long)z * p.colsum_batch + i0 + tid;
+    *d = p.accumulate ? *d + csum : csum;
+  }
+}
+
+// y[m, :] = bias (or 0) through the row map: the pre-fill the split nt product adds onto
+__global__ void __launch_bounds__(256) rows_fill_kernel(float* __restrict__ y, RowMap ym, const float* __restrict__ bias, int M, int N) {
+  pdl_trigger();
+  pdl_wait();
+  const int z = blockIdx.z;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < M * N; idx += gridDim.x * blockDim.x) {
+    const int m = idx / N, n = idx - m * N;
+    y[ym.off(m, z) + n] = bias != nullptr ? __ldg(bias + n) : 0.f;
+  }
+}
+
+static int skinny_max_rows() {       // up to here the weight-streaming kernels; above, the register-tiled ones
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DEVIAS_SKINNY_MAX_ROWS"); v = e ? atoi(e) : 32; }
+  return v;
+}
+
+static int tile_splits(int tiles, int L) {
+  int splits = (2 * sm_count() + tiles - 1) / tiles;          // ~2 CTAs per SM
+  const int max_splits = (L + 4 * kTgK - 1) / (4 * kTgK);     // at least 4 k-chunks per split
+  if (splits > max_splits) splits = max_splits;
+  return splits < 1 ? 1 : splits;
+}
+
 static RowMap make_map(const int64_t* m) {
   RowMap r;
   r.outer = m[0]; r.inner = (int)m[1]; r.ld = m[2]; r.batch = m[3];
@@ -245,6 +402,21 @@ extern "C" int devias_skinny_nt(const float* x, const int64_t* x_map, const floa
   DV_REQUIRE(M > 0 && N > 0 && K > 0 && batch > 0 && K % 4 == 0, "skinny_nt: K must be a multiple of 4");
   DV_REQUIRE(map_ok(x_map) && y_map && y_map[1] > 0 && w_batch % 4 == 0, "skinny_nt: row maps must keep 16-byte alignment");
   DV_REQUIRE((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w)) % 16 == 0, "skinny_nt: x / w must be 16-byte aligned");
+  if (M > skinny_max_rows()) {
+    TileArgs t{};
+    t.A = x; t.B = w; t.C = y; t.am = make_map(x_map); t.cm = make_map(y_map); t.b_batch = w_batch;
+    t.I = M; t.J = N; t.L = K; t.ldb = K;
+    const int tiles = ((M + kTg - 1) / kTg) * ((N + kTg - 1) / kTg) * batch;
+    const int splits = tile_splits(tiles, K);
+    t.l_per_split = ((K + splits - 1) / splits + kTgK - 1) / kTgK * kTgK;
+    int fill_blocks = (M * N + 255) / 256;
+    if (fill_blocks > 4 * sm_count()) fill_blocks = 4 * sm_count();
+    DV_CHECK_CUDA(launch_k(rows_fill_kernel, dim3(fill_blocks, 1, batch), dim3(256), (size_t)0, (cudaStream_t)stream, y, t.cm, bias, M, N));
+    DV_CHECK_CUDA(launch_k(tile_gemm_kernel<0>, dim3((N + kTg - 1) / kTg, (M + kTg - 1) / kTg, batch * splits), dim3(256), (size_t)0,
+                           (cudaStream_t)stream, t, splits));
+    count_launch(2);
+    return DEVIAS_OK;
+  }
   static bool attr = false;
   if (!attr) {
     DV_CHECK_CUDA(cudaFuncSetAttribute(skinny_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSkMT * kSkKC * 4));
@@ -266,6 +438,18 @@ extern "C" int devias_skinny_nn(const float* x, const int64_t* x_map, const floa
   DV_REQUIRE(x && w && y, "null pointer");
   DV_REQUIRE(M > 0 && N > 0 && K > 0 && batch > 0, "skinny_nn: empty problem");
   DV_REQUIRE(x_map && x_map[1] > 0 && y_map && y_map[1] > 0, "skinny_nn: row maps need inner > 0");
+  if (M > skinny_max_rows()) {
+    TileArgs t{};
+    t.A = x; t.B = w; t.C = y; t.am = make_map(x_map); t.cm = make_map(y_map); t.b_batch = w_batch;
+    t.I = M; t.J = N; t.L = K; t.ldb = N;
+    const int tiles = ((M + kTg - 1) / kTg) * ((N + kTg - 1) / kTg) * batch;
+    const int splits = tile_splits(tiles, K);
+    t.l_per_split = ((K + splits - 1) / splits + kTgK - 1) / kTgK * kTgK;
+    DV_CHECK_CUDA(launch_k(tile_gemm_kernel<1>, dim3((N + kTg - 1) / kTg, (M + kTg - 1) / kTg, batch * splits), dim3(256), (size_t)0,
+                           (cudaStream_t)stream, t, splits));
+    count_launch();
+    return DEVIAS_OK;
+  }
   const int mtiles = (M + kSkMT - 1) / kSkMT;
   const dim3 grid((N + kSkNnThreads - 1) / kSkNnThreads, (K + kSkNnKS - 1) / kSkNnKS, batch * mtiles);
   DV_CHECK_CUDA(launch_k(skinny_nn_kernel, dim3(grid), dim3((unsigned)(kSkNnThreads)), (size_t)(0), (cudaStream_t)stream, x, make_map(x_map), w, w_batch, y, make_map(y_map), M, N, K, mtiles));
@@ -281,6 +465,16 @@ extern "C" int devias_skinny_outer(const float* a, const int64_t* a_map, const f
   DV_REQUIRE(M > 0 && I > 0 && J > 0 && batch > 0 && J % 4 == 0, "skinny_outer: J must be a multiple of 4");
   DV_REQUIRE(a_map && a_map[1] > 0 && map_ok(b_map) && c_batch % 4 == 0, "skinny_outer: row maps must keep 16-byte alignment");
   DV_REQUIRE((reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c)) % 16 == 0, "skinny_outer: b / c must be 16-byte aligned");
+  if (M > skinny_max_rows()) {
+    TileArgs t{};
+    t.A = a; t.B = b; t.C = c; t.am = make_map(a_map); t.bm = make_map(b_map); t.c_batch = c_batch;
+    t.I = I; t.J = J; t.L = M; t.ldc = J; t.l_per_split = (M + kTgK - 1) / kTgK * kTgK; t.accumulate = accumulate;
+    t.colsum = colsum; t.colsum_batch = colsum_batch;
+    DV_CHECK_CUDA(launch_k(tile_gemm_kernel<2>, dim3((J + kTg - 1) / kTg, (I + kTg - 1) / kTg, batch), dim3(256), (size_t)0,
+                           (cudaStream_t)stream, t, 1));
+    count_launch();
+    return DEVIAS_OK;
+  }
   const int j4 = J / 4;
   const int threads = j4 >= 256 ? 256 : (j4 + 31) / 32 * 32;
   const dim3 grid((j4 + threads - 1) / threads, (I + kSkOutRows - 1) / kSkOutRows, batch);

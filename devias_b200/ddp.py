@@ -130,15 +130,35 @@ class GradReducer:
         the reducer's reverse-execution parameter order)"""
         return self.param_arena.range_of(params)
 
-    def allreduce_range(self, lo, hi, async_op=False):
-        if self.world <= 1:
+    def buf16(self):
+        """bf16 twin of the gradient arena (created on first use): staging buffer of the compressed exchange"""
+        if getattr(self, '_buf16', None) is None:
+            self._buf16 = torch.zeros(self.arena.numel(), device=self.arena.device, dtype=torch.bfloat16)
+        return self._buf16
+
+    def allreduce_range(self, lo, hi, async_op=False, compress=False):
+        """all-reduce (mean) of arena[lo:hi].  compress=True exchanges bf16: the range is cast into the bf16 twin, reduced there and
+        LEFT there (half the bytes over NVLink; the optimizer pass reads the reduced values from the bf16 buffer, see
+        ArenaAdamW.launch(grad16=...)); `decompress_range` copies them back for consumers that need fp32 gradients."""
+        if self.world <= 1 and not compress:
             return None
+        if compress:
+            from . import ops
+            b = self.buf16()[lo:hi]
+            ops.cast_bf16(self.arena[lo:hi], b)
+            if self.world <= 1:
+                return None
+            assert self._avg, 'the compressed exchange uses the native average of the nccl backend'
+            return dist.all_reduce(b, op=dist.ReduceOp.AVG, group=self.pg, async_op=async_op)
         op = dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
         w = dist.all_reduce(self.arena[lo:hi], op=op, group=self.pg, async_op=async_op)
         if not self._avg:
             assert not async_op, 'SUM + scale needs the synchronous path'
             self.arena[lo:hi].mul_(1.0 / self.world)
         return w
+
+    def decompress_range(self, lo, hi):
+        self.arena[lo:hi].copy_(self.buf16()[lo:hi])
 
     def remove(self):
         for h in self._hooks:

@@ -108,7 +108,7 @@ class GraphedTrainStep:
     """
 
     def __init__(self, model, train_criterion, optimizer, batches, reducer=None, warmup=3, split_block=3, scene_model=None,
-                 update_freq=1, cuts=None):
+                 update_freq=1, cuts=None, grad_exchange='fp32'):
         from . import _lib
         from .optim import ArenaAdamW
         self.model, self.crit, self.opt, self.reducer = model, train_criterion, optimizer, reducer
@@ -116,6 +116,11 @@ class GraphedTrainStep:
         self.batches = list(batches)
         self.update_freq = int(update_freq)
         self.arena_mode = isinstance(optimizer, ArenaAdamW)
+        assert grad_exchange in ('fp32', 'bf16')
+        #: 'bf16': every range is cast to bf16, all-reduced in bf16 (half the NVLink bytes) and consumed from the bf16 buffer by the
+        #: arena optimizer pass (torch optimizers / gradient clipping get it copied back to fp32 first)
+        self.compress = grad_exchange == 'bf16' and reducer is not None
+        self._grad16 = self.compress and self.arena_mode and not (getattr(optimizer, 'max_norm', 0) > 0)
         assert self.update_freq == 1 or self.arena_mode, 'gradient accumulation across replays needs the gradient arena (ArenaAdamW)'
         self.split = reducer is not None
         self._taps, self._hooks, self._active = {}, [], False
@@ -268,11 +273,17 @@ class GraphedTrainStep:
 
     def _exchange_all(self):
         if self.split:
-            self.reducer.allreduce_all()
+            if self.compress:
+                self.reducer.allreduce_range(0, self.reducer.arena.numel(), compress=True)
+                if not self._grad16:
+                    self.reducer.decompress_range(0, self.reducer.arena.numel())
+            else:
+                self.reducer.allreduce_all()
 
     def _update(self):
         if self.arena_mode:
-            self.opt.launch()                      # hyper-parameters come from device memory (sync_hyper before the replay)
+            # hyper-parameters come from device memory (sync_hyper before the replay)
+            self.opt.launch(grad16=self.reducer.buf16() if self._grad16 else None)
             return
         self.opt.step()
         if self.split:
@@ -297,11 +308,13 @@ class GraphedTrainStep:
                 g.replay()
                 if do_update:
                     last = i == len(gs) - 1
-                    w = red.allreduce_range(*self.ranges[i], async_op=(red._avg and not last))
+                    w = red.allreduce_range(*self.ranges[i], async_op=(red._avg and not last), compress=self.compress)
                     if w is not None and not last:
                         works.append(w)
             for w in works:
                 w.wait()
+            if do_update and self.compress and not self._grad16:
+                red.decompress_range(0, red.arena.numel())
         if do_update and self.update_graph is not None:
             if self.arena_mode:
                 self.opt.sync_hyper()

@@ -86,8 +86,9 @@ class ArenaAdamW(torch.optim.Optimizer):
         ev.record()
         self._host_ev[slot] = ev
 
-    def launch(self, zero_grad=True):
-        """the device work of one update (capturable): [sum of squares of the gradient arena] + the fused update pass"""
+    def launch(self, zero_grad=True, grad16=None):
+        """the device work of one update (capturable): [sum of squares of the gradient arena] + the fused update pass.
+        grad16: bf16 arena holding the (all-reduced) gradient values to use instead of the fp32 arena's"""
         a = self.arena
         s = torch.cuda.current_stream().cuda_stream
         lib = _lib.lib()
@@ -99,7 +100,7 @@ class ArenaAdamW(torch.optim.Optimizer):
         _lib.check(lib.devias_adamw_arena(a.data.data_ptr(), a.grad.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
                                           a._shadow.data_ptr(), self.seg_start.data_ptr(), self.seg_group.data_ptr(), self.n_seg,
                                           self.hyper.data_ptr(), self.sumsq.data_ptr() if clip else None, a.numel,
-                                          int(zero_grad), s), 'adamw_arena')
+                                          int(zero_grad), None if grad16 is None else grad16.data_ptr(), s), 'adamw_arena')
         a.mark_fresh()                                        # the pass rewrote the bf16 shadow of every parameter
 
     @torch.no_grad()

@@ -199,11 +199,13 @@ int devias_skinny_outer(const float* a, const int64_t* a_map, const float* b, co
  *   hyper[0] = 1 - beta1^t, [1] = 1 - beta2^t, [2] = beta1, [3] = beta2, [4] = eps, [5] = max_norm (<= 0: off),
  *   [6] = gradient pre-scale, [7] unused, then per group g: [8 + 2g] = lr, [9 + 2g] = weight_decay.
  * grad_sumsq (device fp32 scalar, may be NULL): sum of squares of the whole gradient arena (devias_sumsq_f32); with
- * max_norm > 0 the gradient is scaled by min(1, max_norm / (|pre-scale| * sqrt(sumsq) + 1e-6)) = torch clip_grad_norm_. */
+ * max_norm > 0 the gradient is scaled by min(1, max_norm / (|pre-scale| * sqrt(sumsq) + 1e-6)) = torch clip_grad_norm_.
+ * grad_bf16 (may be NULL): when given, the gradient VALUES are read from this bf16 arena of n elements (the buffer a bf16 gradient
+ * all-reduce left its result in) instead of `grad`; `grad` is still the arena that gets zero-filled. */
 int devias_sumsq_f32(const float* x, int64_t n, float* out, void* stream);
 int devias_adamw_arena(float* param, float* grad, float* exp_avg, float* exp_avg_sq, void* param_bf16,
                        const int32_t* seg_start, const int32_t* seg_group, int n_seg, const float* hyper,
-                       const float* grad_sumsq, int64_t n, int zero_grad, void* stream);
+                       const float* grad_sumsq, int64_t n, int zero_grad, const void* grad_bf16, void* stream);
 
 #ifdef __cplusplus
 }

@@ -87,3 +87,28 @@ def test_fame_on_device_matches_cpu():
     assert gpu.is_cuda and (gpu.cpu() == cpu).float().mean() > 0.995
     out_v, out_l, (m, mpf) = f(vids.cuda(), torch.arange(2).cuda())
     assert out_v.is_cuda and m.is_cuda and m.shape == (2, 196) and mpf.shape == (2, 1568)
+
+
+def test_blur_and_hsv_known_answers_from_the_published_definitions():
+    """pins devias_b200.fame AND the numpy oracle on hand-computed known answers of the definitions the reference delegates to kornia
+    for (tests/golden/fame_known_answers.json states the sources: kornia's docstring kernels, 'reflect' border, the HSV sextants)"""
+    import json
+    import os
+    from devias_b200 import fame
+    ka = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'fame_known_answers.json')))
+    for case in ka['gaussian_kernel1d']:
+        k = fame.gaussian_kernel1d(case['ksize'], case['sigma']).numpy()
+        assert np.abs(k - np.array(case['kernel'])).max() < case['tol']
+    for case in ka['blur_rows_k3_s2.5']:
+        # a 5 x 5 image whose rows all equal `row`: the vertical pass of the separable blur leaves it unchanged (kernel sums to 1)
+        img = np.tile(np.array(case['row'], np.float32), (5, 1))
+        got = fame.gaussian_blur2d(torch.from_numpy(img)[None, None], 3, 2.5)[0, 0].numpy()
+        ora = FO.gaussian_blur(img, 3, 2.5)
+        for out in (got, ora):
+            assert np.abs(out - np.array(case['out'])[None, :]).max() < 1e-4, (case, out[0])
+    for case in ka['rgb_to_hsv']:
+        rgb = np.array(case['rgb'], np.float32).reshape(3, 1, 1)
+        got = fame.rgb_to_hsv(torch.from_numpy(rgb)[None])[0].numpy().reshape(3)
+        h, s, v = FO.rgb_to_hsv(rgb)
+        for out in (got, np.array([h.item(), s.item(), v.item()])):
+            assert np.abs(out - np.array(case['hsv'])).max() < 2e-6, (case, out)

@@ -43,7 +43,7 @@ def test_linear_3d_input_and_any_number_of_rows(rows):
     y = slot_linear.linear(xl, w, b)
     dy = torch.randn_like(y)
     gx, gw, gb = torch.autograd.grad(y, [xl, w, b], dy)
-    assert _lib.launch_count() - n0 == 3, 'forward + two backward kernels of csrc/skinny.cu'
+    assert 3 <= _lib.launch_count() - n0 <= 4, 'forward (+ its pre-fill) and two backward kernels of csrc/skinny.cu'
     xd, wd, bd = (t.detach().double().requires_grad_(True) for t in (xl, w, b))
     yr = F.linear(xd, wd, bd)
     rx, rw, rb = torch.autograd.grad(yr, [xd, wd, bd], dy.double())
