@@ -55,6 +55,7 @@ def parse():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--cuts', default='8,4,1', help='data-parallel step: encoder blocks at which the backward graph is cut')
     ap.add_argument('--grad-exchange', default='bf16', choices=['fp32', 'bf16'], help='data-parallel gradient all-reduce precision')
+    ap.add_argument('--no-exchange', action='store_true', help='diagnostic: N independent replicas, no gradient all-reduce (isolates what the collective costs)')
     ap.add_argument('--no-secondary', action='store_true', help='skip the UCF-101 B=8 secondary line')
     ap.add_argument('--no-extras', action='store_true', help='skip slot grid / eval sweep / gpu reference (N=1 extras)')
     ap.add_argument('--torch-adamw', action='store_true', help='torch fused AdamW instead of the arena optimizer pass')
@@ -229,7 +230,7 @@ def measure_train(name, cfg, args, dev, world, rank, with_roofline=True, with_e2
     decay = [p for n_, p in model.named_parameters() if p.dim() > 1 and n_ not in model.no_weight_decay()]
     rest = [p for n_, p in model.named_parameters() if not (p.dim() > 1 and n_ not in model.no_weight_decay())]
     groups = [dict(params=decay, weight_decay=0.05), dict(params=rest, weight_decay=0.0)]
-    reducer = GradReducer(model) if world > 1 else None
+    reducer = GradReducer(model) if (world > 1 and not args.no_exchange) else None
     if args.torch_adamw:
         opt = torch.optim.AdamW(groups, lr=1e-4, fused=True, capturable=True)
     else:

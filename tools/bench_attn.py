@@ -8,6 +8,8 @@ N, H = 1568, 12
 qkv = (torch.randn(B * N, 3 * H * 64, device='cuda') * 1.2).bfloat16()
 dout = torch.randn(B * N, H * 64, device='cuda').bfloat16()
 def t(fn, n=20):
+    if os.environ.get('DEVIAS_ONESHOT'):       # one launch per case: `ncu -c <cases>` then captures every shape exactly once
+        fn(); torch.cuda.synchronize(); return 1.0
     for _ in range(3): fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

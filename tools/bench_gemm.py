@@ -9,6 +9,8 @@ M = B * 1568
 bf = lambda *s: (torch.randn(*s, device='cuda') * 0.1).bfloat16()
 f32 = lambda *s: torch.randn(*s, device='cuda')
 def t(fn, n=20):
+    if os.environ.get('DEVIAS_ONESHOT'):       # one launch per case: `ncu -c <cases>` then captures every shape exactly once
+        fn(); torch.cuda.synchronize(); return 1.0
     for _ in range(3): fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
