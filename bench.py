@@ -53,7 +53,7 @@ def parse():
     ap.add_argument('--batch', type=int, default=0, help='clips per GPU (default: the workload recipe)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
-    ap.add_argument('--cuts', default='8,4,1', help='data-parallel step: encoder blocks at which the backward graph is cut')
+    ap.add_argument('--cuts', default='1', help="data-parallel step: encoder blocks at which the backward graph is cut ('none': one piece)")
     ap.add_argument('--grad-exchange', default='bf16', choices=['fp32', 'bf16'], help='data-parallel gradient all-reduce precision')
     ap.add_argument('--no-exchange', action='store_true', help='diagnostic: N independent replicas, no gradient all-reduce (isolates what the collective costs)')
     ap.add_argument('--no-secondary', action='store_true', help='skip the UCF-101 B=8 secondary line')

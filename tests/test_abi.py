@@ -78,3 +78,51 @@ def test_model_interface_matches_reference_contract():
     with pytest.raises(ValueError):
         with contextlib.redirect_stdout(io.StringIO()):
             slot_vit_base_patch16_224(num_classes=10, slot_matching_method='bogus')
+
+
+def test_reference_checkpoint_loader_walk_and_layer_decay_names():
+    """INTEGRATION.md claims: (1) the reference's own checkpoint loader (utils/utils.py:330-348: a recursive walk over
+    `_modules` calling `_load_from_state_dict` with the running prefix) fills the drop-in model completely from a state_dict with
+    the reference's keys -- a VideoMAE pre-training checkpoint (encoder keys only) leaves exactly the slot / head parameters
+    missing; (2) parameter NAMES map to the layer-decay groups of utils/optim_factory.py:24-35."""
+    from functools import partial
+    from devias_b200.modeling_slot import VisionTransformer
+    from oracle import devias_oracle as O
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = VisionTransformer(patch_size=16, embed_dim=768, depth=2, num_heads=12, mlp_ratio=4, qkv_bias=True,
+                              norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), num_classes=11, num_latents=2, agg_depth=2,
+                              agg_weights_tie=True, slot_matching_method='matching', init_scale=1.0)
+    sd = O.synth_state_dict(num_classes=11, num_latents=2, agg_depth=2, depth=2, seed=5)
+
+    def walk_load(model, state_dict):          # the loader of utils/utils.py:330-348, restated
+        missing, unexpected, errors = [], [], []
+        state_dict = dict(state_dict)
+
+        def load(module, prefix=''):
+            module._load_from_state_dict(state_dict, prefix, {}, True, missing, unexpected, errors)
+            for name, child in module._modules.items():
+                if child is not None:
+                    load(child, prefix + name + '.')
+        load(model)
+        return missing, errors
+
+    missing, errors = walk_load(m, sd)
+    assert not missing and not errors
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, sd[k]), k
+    encoder_only = {k: v for k, v in sd.items() if k.startswith(('patch_embed.', 'blocks.', 'norm.'))}
+    missing, errors = walk_load(m, encoder_only)
+    assert not errors and missing and all(k.startswith(('agg_block.', 'mask_predictor.', 'head.')) for k in missing)
+
+    def layer_id(name, num_layers):            # utils/optim_factory.py:24-35 (get_num_layer_for_vit), restated
+        if name in ('cls_token', 'mask_token', 'pos_embed') or name.startswith('patch_embed'):
+            return 0
+        if name.startswith('rel_pos_bias'):
+            return num_layers - 1
+        if name.startswith('blocks'):
+            return int(name.split('.')[1]) + 1
+        return num_layers - 1
+    n = m.get_num_layers() + 2
+    ids = {k: layer_id(k, n) for k, _ in m.named_parameters()}
+    assert ids['patch_embed.proj.weight'] == 0 and ids['blocks.1.mlp.fc1.weight'] == 2 and ids['head.weight'] == n - 1
+    assert any('agg_block' in k for k in ids)          # the 'agg_block' substring selects agg_block_scale (optim_factory.py:66-78)

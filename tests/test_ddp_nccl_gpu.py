@@ -62,7 +62,16 @@ def _worker(rank, world, port, mode, q):
         crit = TrainLoss(None, 'KL', C)
         red = GradReducer(m, bucket_mb=8.0, first_bucket_mb=1.0)
         snap = {k: v.detach().clone() for k, v in m.state_dict().items()}
-        if mode == 'eager':
+        if mode == 'torch_ddp':
+            # the drop-in model is an ordinary nn.Module -- the reference's own wrapping
+            # (torch.nn.parallel.DistributedDataParallel, run_slot_finetuning.py:552-563) works unchanged on it
+            red.remove()
+            ddp = torch.nn.parallel.DistributedDataParallel(m, device_ids=[rank], find_unused_parameters=True)
+            opt = torch.optim.SGD(m.parameters(), lr=0.05)
+            for _ in range(2):
+                engine.train_step(ddp, None, crit, opt, mine['clip'], mine['target'], (mine['fg'], mine['fgf']),
+                                  teacher_logits=mine['teacher'])
+        elif mode == 'eager':
             opt = torch.optim.SGD(m.parameters(), lr=0.05)
             for _ in range(2):
                 engine.train_step(m, None, crit, opt, mine['clip'], mine['target'], (mine['fg'], mine['fgf']),
@@ -104,7 +113,7 @@ def _worker(rank, world, port, mode, q):
                 rel = float((flat.double() - want).norm() / want.norm())
                 q.put((rank, identical, rel))
                 return
-            if mode == 'eager':
+            if mode in ('eager', 'torch_ddp'):
                 ropt = torch.optim.SGD(ref.parameters(), lr=0.05)
             else:
                 ropt = torch.optim.AdamW(ref.parameters(), lr=1e-3, weight_decay=0.05)
@@ -121,7 +130,7 @@ def _worker(rank, world, port, mode, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('mode', ['eager', 'graphed', 'graphed_bf16'])
+@pytest.mark.parametrize('mode', ['eager', 'graphed', 'graphed_bf16', 'torch_ddp'])
 def test_two_ranks_identical_and_equal_to_single_process(mode):
     if torch.cuda.device_count() < 2:
         pytest.skip('needs 2 GPUs (run with gpurun --gpus 2)')
@@ -139,4 +148,4 @@ def test_two_ranks_identical_and_equal_to_single_process(mode):
     assert all(r[1] for r in res), 'ranks ended the step with different parameters'
     # per-rank batches of B clips vs one batch of 2B: same gradients up to bf16 / summation-order noise (amplified by Adam's
     # normalisation in the graphed case)
-    assert res[0][2] <= {'eager': 0.02, 'graphed': 0.06, 'graphed_bf16': 0.02}[mode], res[0][2]
+    assert res[0][2] <= {'eager': 0.02, 'graphed': 0.06, 'graphed_bf16': 0.02, 'torch_ddp': 0.02}[mode], res[0][2]
