@@ -59,6 +59,8 @@ _SIGS = {
     'devias_debug_token_stream': (c_int, [_P, c_int, c_int, c_int, _P, _P]),
     'devias_skinny_nt': (c_int, [_P, _P, _P, c_int64, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     'devias_skinny_nn': (c_int, [_P, _P, _P, c_int64, _P, _P, c_int, c_int, c_int, c_int, _P]),
+    'devias_train_loss_fwd': (c_int, [_P] * 9 + [c_int] * 9 + [c_float] * 3 + [_P, _P, _P]),
+    'devias_train_loss_bwd': (c_int, [_P] * 9 + [c_int] * 9 + [c_float] * 3 + [_P] * 5 + [_P]),
     'devias_sumsq_f32': (c_int, [_P, c_int64, _P, _P]),
     'devias_adamw_arena': (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, _P, _P, c_int64, c_int, _P, _P]),
     'devias_skinny_outer': (c_int, [_P, _P, _P, _P, _P, c_int64, _P, c_int64, c_int, c_int, c_int, c_int, c_int, _P]),

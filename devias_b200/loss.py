@@ -9,6 +9,46 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 
+class _FusedTrainLossFn(torch.autograd.Function):
+    """csrc/train_loss.cu: the whole objective in one launch, its gradients in one more (include/devias_b200.h)"""
+
+    @staticmethod
+    def forward(ctx, head, attn, maskp, slots, target, teacher, fg, fgf, cfg):
+        from . import _lib
+        C, scene_ce, w_scene, w_mp, w_md = cfg
+        B = target.shape[0]
+        S = head.shape[0] // B
+        H = attn.shape[0] // B
+        head, attn, maskp, slots = head.contiguous(), attn.contiguous(), maskp.contiguous(), slots.contiguous()
+        teacher, fg, fgf, target = teacher.contiguous(), fg.contiguous(), fgf.contiguous(), target.contiguous()
+        var = (teacher.min() - 1.0).reshape(1)                                      # train_loss.py:103 (batch-wide scalar)
+        out6 = torch.empty(6, device=head.device, dtype=torch.float32)
+        idx = torch.empty(B, 2, device=head.device, dtype=torch.int64)
+        dims = (B, S, head.shape[1], C, H, attn.shape[-1], maskp.shape[-1], slots.shape[-1], int(scene_ce))
+        s = torch.cuda.current_stream().cuda_stream
+        _lib.check(_lib.lib().devias_train_loss_fwd(head.data_ptr(), attn.data_ptr(), maskp.data_ptr(), slots.data_ptr(), target.data_ptr(),
+                                                    teacher.data_ptr(), var.data_ptr(), fg.data_ptr(), fgf.data_ptr(), *dims,
+                                                    float(w_scene), float(w_mp), float(w_md), out6.data_ptr(), idx.data_ptr(), s),
+                   'train_loss_fwd')
+        ctx.save_for_backward(head, attn, maskp, slots, target, teacher, var, fg, fgf)
+        ctx.dims, ctx.weights = dims, (float(w_scene), float(w_mp), float(w_md))
+        ctx.mark_non_differentiable(idx)
+        return out6[5], out6[:5], idx
+
+    @staticmethod
+    def backward(ctx, gtotal, gparts, gidx):
+        from . import _lib
+        head, attn, maskp, slots, target, teacher, var, fg, fgf = ctx.saved_tensors
+        g = gtotal.reshape(1).float().contiguous()
+        dhead, dattn, dmaskp, dslots = (torch.empty_like(t) for t in (head, attn, maskp, slots))
+        s = torch.cuda.current_stream().cuda_stream
+        _lib.check(_lib.lib().devias_train_loss_bwd(head.data_ptr(), attn.data_ptr(), maskp.data_ptr(), slots.data_ptr(), target.data_ptr(),
+                                                    teacher.data_ptr(), var.data_ptr(), fg.data_ptr(), fgf.data_ptr(), *ctx.dims,
+                                                    *ctx.weights, g.data_ptr(), dhead.data_ptr(), dattn.data_ptr(), dmaskp.data_ptr(),
+                                                    dslots.data_ptr(), s), 'train_loss_bwd')
+        return dhead, dattn, dmaskp, dslots, None, None, None, None, None
+
+
 class TrainLoss(nn.Module):
     def __init__(self, criterion, scene_criterion, num_action_classes: int, slot_matching_method='matching',
                  scene_loss_weight=2000, mask_prediction_loss_weight=1, mask_distill_loss_weight=3, sync_items=False):
@@ -23,6 +63,8 @@ class TrainLoss(nn.Module):
         self.scene_loss_weight = scene_loss_weight
         #: True reproduces the reference's five `.item()` host syncs per step (python floats in the dict)
         self.sync_items = sync_items
+        #: CUDA inputs take the fused kernels (csrc/train_loss.cu); False evaluates the torch expressions below instead (tests)
+        self.fused = True
         if slot_matching_method != 'matching':
             raise NotImplementedError("only the live 'matching' branch is provided (hard_select crashes in the reference, "
                                       "SURVEY.md R8)")
@@ -43,6 +85,20 @@ class TrainLoss(nn.Module):
         _, (action_output, _, attn), (slots_head, slots, mask_predictions) = student_output
         bs = target.shape[0]
         S = slots_head.shape[0] // bs
+        if self.fused and slots_head.is_cuda and 2 <= S <= 8 and self.scene_criterion in ('KL', 'CE'):
+            # one kernel launch for the objective, one for its gradients (csrc/train_loss.cu); the torch expressions below are the
+            # same arithmetic and serve CPU tensors (unit tests against the reference's values)
+            fg, fg_frames = fg_mask
+            total, parts5, idx = _FusedTrainLossFn.apply(
+                slots_head.float(), attn.float(), mask_predictions.float().reshape(bs * S, -1), slots.float().reshape(bs * S, -1),
+                target, teacher_outputs[1].float(), fg.float(), fg_frames.float(),
+                (self.num_action_classes, self.scene_criterion == 'CE', self.scene_loss_weight, self.mask_prediction_loss_weight,
+                 self.mask_distill_loss_weight))
+            act_rows = slots_head.view(bs, S, -1)[torch.arange(bs, device=target.device), idx[:, 0]]
+            names = ('action_loss', 'scene_loss', 'cosine_loss', 'mask_prediction_loss', 'mask_distill_loss')
+            parts5 = parts5.detach()
+            parts = {k: (parts5[i].item() if self.sync_items else parts5[i]) for i, k in enumerate(names)}
+            return total, act_rows, parts
         H = attn.size(0) // bs
         C = self.num_action_classes
         slots_head = slots_head.float()

@@ -207,6 +207,26 @@ int devias_adamw_arena(float* param, float* grad, float* exp_avg, float* exp_avg
                        const int32_t* seg_start, const int32_t* seg_group, int n_seg, const float* hyper,
                        const float* grad_sumsq, int64_t n, int zero_grad, const void* grad_bf16, void* stream);
 
+/* ---- the training objective ('matching' branch of utils/loss/train_loss.py:85-187) in one launch per direction ----------------
+ * Per clip: softmax of the S slot rows of slots_head [B*S, width = n_action + scene classes], assignment of distinct (action, scene)
+ * slots minimising -p[i, target] - p[j, scene_target] (:112-122; scene_target = n_action + argmax teacher), then
+ *   out6[0] action  = CE(head[i], target)                                   out6[1] scene = w_scene * KL(teacher_full || head[j]) / width
+ *   out6[2] cosine  = mean_{i != j} <slots_i, slots_j> (normalised)                          (scene_ce != 0: CE(head[j], scene_target))
+ *   out6[3] maskpred = w_maskpred * BCEwithLogits(maskp[i], fg)             out6[4] distill = w_distill * MSE(mean_heads attn[i], fgf)
+ *   out6[5] total; all summed over the batch / batch.  slot_idx int64 [B, 2] = (i, j).  teacher_full = [var x n_action | teacher]
+ * with var_scalar a DEVICE scalar = min over the whole batch of the teacher logits - 1 (:103).
+ * attn fp32 [B*heads, S, n_tokens], maskp [B*S, n_patches], slots [B*S, dim], teacher [B, width - n_action], fg [B, n_patches],
+ * fgf [B, n_tokens], target int64 [B].  The backward writes the FULL gradients of out6[5] * grad_total[0] (zeros included). */
+int devias_train_loss_fwd(const float* head, const float* attn, const float* maskp, const float* slots, const int64_t* target,
+                          const float* teacher, const float* var_scalar, const float* fg, const float* fgf, int batch,
+                          int slots_per_clip, int width, int n_action, int heads, int n_tokens, int n_patches, int dim, int scene_ce,
+                          float w_scene, float w_maskpred, float w_distill, float* out6, int64_t* slot_idx, void* stream);
+int devias_train_loss_bwd(const float* head, const float* attn, const float* maskp, const float* slots, const int64_t* target,
+                          const float* teacher, const float* var_scalar, const float* fg, const float* fgf, int batch,
+                          int slots_per_clip, int width, int n_action, int heads, int n_tokens, int n_patches, int dim, int scene_ce,
+                          float w_scene, float w_maskpred, float w_distill, const float* grad_total, float* dhead, float* dattn,
+                          float* dmaskp, float* dslots, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
