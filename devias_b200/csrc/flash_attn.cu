@@ -615,8 +615,8 @@ __global__ void __launch_bounds__(256) flash_bwd_prep_kernel(const __nv_bfloat16
   tile[128 + row] = split3_bf16(-s);    // delta block
 }
 
-// dqkv[:, 0:D] = bf16(scale * dq_acc); the accumulator is handed back zero-filled, ready for the next backward call
-__global__ void __launch_bounds__(256) flash_dq_convert_kernel(float* __restrict__ acc, __nv_bfloat16* __restrict__ dqkv,
+// dqkv[:, 0:D] = bf16(scale * dq_acc)
+__global__ void __launch_bounds__(256) flash_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dqkv,
                                                                long long rows, int D, long long ld, float scale) {
   pdl_trigger();
   pdl_wait();
@@ -624,10 +624,8 @@ __global__ void __launch_bounds__(256) flash_dq_convert_kernel(float* __restrict
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
     const long long row = i / (D / 8);
     const int c8 = (int)(i % (D / 8));
-    float4* src = reinterpret_cast<float4*>(acc + row * D + c8 * 8);
-    const float4 a = __ldcs(src), c = __ldcs(src + 1);
-    src[0] = make_float4(0.f, 0.f, 0.f, 0.f);
-    src[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 a = __ldcs(reinterpret_cast<const float4*>(acc + row * D + c8 * 8));
+    const float4 c = __ldcs(reinterpret_cast<const float4*>(acc + row * D + c8 * 8) + 1);
     *reinterpret_cast<uint4*>(dqkv + row * ld + c8 * 8) =
         make_uint4(pack_bf16(a.x * scale, a.y * scale), pack_bf16(a.z * scale, a.w * scale), pack_bf16(c.x * scale, c.y * scale),
                    pack_bf16(c.z * scale, c.w * scale));
@@ -673,8 +671,8 @@ extern "C" int devias_flash_attn_fwd(const void* qkv, void* out, float* lse2, in
 }
 
 extern "C" int devias_flash_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse2, void* dqkv,
-                                     void* aug_ws, float* dq_ws, int dq_ws_is_zero, int batch, int seq, int heads, int head_dim,
-                                     float scale, void* stream) {
+                                     void* aug_ws, float* dq_ws, int batch, int seq, int heads, int head_dim, float scale,
+                                     void* stream) {
   using namespace dv;
   DV_REQUIRE(qkv && out && dout && lse2 && dqkv && aug_ws && dq_ws, "null pointer");
   DV_REQUIRE(head_dim == 64, "head_dim 64 only (ViT-B/16)");
@@ -702,7 +700,7 @@ extern "C" int devias_flash_attn_bwd(const void* qkv, const void* out, const voi
     DV_CHECK_CUDA(cudaFuncSetAttribute(flash_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FbSmem::BYTES));
     attr_done = true;
   }
-  if (!dq_ws_is_zero) DV_CHECK_CUDA(cudaMemsetAsync(dq_ws, 0, (size_t)batch * seq * D * sizeof(float), s));
+  DV_CHECK_CUDA(cudaMemsetAsync(dq_ws, 0, (size_t)batch * seq * D * sizeof(float), s));
   const float scale_log2 = scale * 1.4426950408889634f;
   {
     const long long total = (long long)batch * Npad * heads;

@@ -17,7 +17,7 @@
 // of dW = dX0^T im2col(clip) over the same 5-D boxes returned exact zeros on sm_100a; the 16-bit kinds transpose, the 32-bit one
 // does not) -- an in-kernel fp32 -> bf16 conversion stage would be needed to drop the patch matrix there too.
 //
-//   CTA  = (98-token tile, 256-column block of the 768 outputs); 96 k-chunks of 16 through a 6-stage TMA ring
+//   CTA  = (98-token tile, 256-column block of the 768 outputs); 96 k-chunks of 16 through a 3-stage TMA ring, two CTAs per SM
 //   warp 0 : TMA producer      warp 1 : tcgen05.mma issuer (M = 128 rows of which 98 are tokens, N = 256, K = 8 per instruction,
 //                              two per chunk)
 //   warps 2..5 : epilogue -- TMEM -> registers, + bias + position rows (bulk tensor load of the [32 x 32] box), 128B-swizzled
@@ -30,7 +30,7 @@ namespace dv {
 constexpr int kPeTok = 98;            // tokens per tile: 7 patch rows x 14 patch columns of one frame pair
 constexpr int kPeBN = 256;
 constexpr int kPeKC = 16;             // fp32 elements per k-chunk = one 64-byte swizzle row = the 16 dx of one patch row
-constexpr int kPeStages = 6;
+constexpr int kPeStages = 3;            // 104 KiB per CTA: two CTAs per SM (their TMA streams and epilogues overlap)
 constexpr int kPeThreads = 192;
 struct PeSmem {
   static constexpr int A_BYTES = 128 * 64;                   // 98 rows are written by the TMA box, 128 are addressed by the MMA
@@ -82,7 +82,7 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* s
                : "memory");
 }
 
-__global__ void __launch_bounds__(kPeThreads, 1)
+__global__ void __launch_bounds__(kPeThreads, 2)
 patch_embed_fwd_kernel(const __grid_constant__ CUtensorMap tmClip, const __grid_constant__ CUtensorMap tmW,
                        const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmPos, const PeParams p) {
   pdl_trigger();

@@ -294,8 +294,9 @@ __global__ void __launch_bounds__(256) tile_gemm_kernel(const TileArgs p, int sp
     b_vec = ok && ((reinterpret_cast<uintptr_t>(b_row) & 15) == 0);
   }
   float csum = 0.f;                                   // MODE 2: column sums of a (thread tid < 64 <-> i = i0 + tid)
-  for (int l0 = l_begin; l0 < l_end; l0 += kTgK) {
-    float4 av = make_float4(0.f, 0.f, 0.f, 0.f), bv = av;
+  auto fetch = [&](int l0, float4& av, float4& bv) {  // this thread's 16 bytes of the A and B chunk starting at l0
+    av = make_float4(0.f, 0.f, 0.f, 0.f);
+    bv = av;
     if (MODE == 0 || MODE == 1) {
       if (a_row != nullptr) av = ld4_guard(a_row + l0 + ll4, l_end - (l0 + ll4), a_vec && ((l0 + ll4) & 3) == 0);
     } else {
@@ -314,6 +315,10 @@ __global__ void __launch_bounds__(256) tile_gemm_kernel(const TileArgs p, int sp
         bv = ld4_guard(src, p.J - (j0 + sc4), (reinterpret_cast<uintptr_t>(src) & 15) == 0);
       }
     }
+  };
+  float4 av, bv;
+  if (l_begin < l_end) fetch(l_begin, av, bv);
+  for (int l0 = l_begin; l0 < l_end; l0 += kTgK) {
     __syncthreads();                                  // the previous chunk has been consumed
     if (MODE == 0 || MODE == 1) {
       As[ll4][lr] = av.x; As[ll4 + 1][lr] = av.y; As[ll4 + 2][lr] = av.z; As[ll4 + 3][lr] = av.w;
@@ -326,6 +331,7 @@ __global__ void __launch_bounds__(256) tile_gemm_kernel(const TileArgs p, int sp
       *reinterpret_cast<float4*>(&Bs[sl][sc4]) = bv;
     }
     __syncthreads();
+    if (l0 + kTgK < l_end) fetch(l0 + kTgK, av, bv);  // next chunk in flight while this one is multiplied
 #pragma unroll
     for (int l = 0; l < kTgK; ++l) {
       const float4 a4 = *reinterpret_cast<const float4*>(&As[l][ti * 4]);

@@ -4,8 +4,9 @@ SURVEY.md section 8f row N4).  Same constructor and `forward(videos, label, cent
 
     returns (videos', labels', (fg_mask [B, 196], fg_mask_per_frame [B, 8*196])[, center_frame'])
 
-The two kornia calls of the reference are restated from kornia's published definitions (kornia is not in this image, so
-this file's parity against kornia itself is UNPINNED; tests pin it against an independent numpy restatement in oracle/):
+The two kornia calls of the reference are restated from kornia's published definitions.  kornia is not in this image, so parity
+is pinned on hand-computed known answers of those definitions (tests/golden/fame_known_answers.json: kornia's docstring Gaussian
+kernels, the 'reflect' border, the HSV sextants) and on an independent numpy restatement in oracle/ -- not on kornia's outputs:
   * kornia.filters.GaussianBlur2d((k, k), (k/3, k/3)): separable normalised Gaussian, 'reflect' border;
   * kornia.color.rgb_to_hsv: h in [0, 2 pi), s = delta / (max + 1e-8), v = max.
 Random draws follow the reference call for call (randperm on the video's device, rand on the CPU), so a seeded CPU run

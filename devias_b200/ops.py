@@ -251,9 +251,6 @@ def flash_attn_fwd(qkv: torch.Tensor, B: int, N: int, H: int, need_lse=True):
     return out, lse2
 
 
-_dq_ws = {}    # (device index, elements) -> fp32 dQ accumulator that every backward call hands back zero-filled
-
-
 def flash_attn_bwd(qkv, out, dout, lse2, B: int, N: int, H: int):
     """-> dqkv bf16 [B*N, 3*H*64]  (include/devias_b200.h: devias_flash_attn_bwd)"""
     _need_cuda(qkv, out, dout, lse2)
@@ -261,17 +258,9 @@ def flash_attn_bwd(qkv, out, dout, lse2, B: int, N: int, H: int):
     npad = (N + 127) // 128 * 128
     dqkv = torch.empty_like(qkv)
     aug = torch.empty(B * H * npad * 16, device=qkv.device, dtype=torch.bfloat16)     # [lse | delta] k-step operand blocks
-    key = (qkv.device.index, B * N * H * 64)
-    dq = _dq_ws.get(key)
-    fresh = dq is None
-    if fresh:
-        if torch.cuda.is_current_stream_capturing():
-            dq = torch.empty(key[1], device=qkv.device, dtype=torch.float32)      # graph-private, zeroed inside the call
-        else:
-            dq = _dq_ws[key] = torch.zeros(key[1], device=qkv.device, dtype=torch.float32)
-            fresh = False
+    dq = torch.empty(B * N * H * 64, device=qkv.device, dtype=torch.float32)
     rc = _lib.lib().devias_flash_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse2.data_ptr(), dqkv.data_ptr(),
-                                          aug.data_ptr(), dq.data_ptr(), int(not fresh), B, N, H, 64, 0.125, _stream())
+                                          aug.data_ptr(), dq.data_ptr(), B, N, H, 64, 0.125, _stream())
     _lib.check(rc, 'flash_attn_bwd')
     return dqkv
 

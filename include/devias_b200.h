@@ -80,13 +80,12 @@ int devias_gemm_bf16(const void* a, int64_t lda, int a_mn_major, const void* b, 
  * [12, seq, seq] probabilities.  lse2: fp32 [batch, heads, seq_pad] (seq_pad = seq rounded up to 128), log2-domain
  * log-sum-exp kept for the backward (may be NULL for inference).
  * Backward: dqkv bf16 [batch*seq, 3*heads*64] from dout.  Caller-provided scratch: aug_ws bf16 [batch*heads*seq_pad*16]
- * (the log-sum-exp / row-term operand blocks the kernel's extra MMA k-step reads) and dq_ws fp32 [batch*seq*heads*64], the dQ
- * accumulator (TMA reduce-add target): zero-filled by the call unless dq_ws_is_zero != 0, and ALWAYS left zero-filled again by the
- * final conversion pass -- a caller that keeps one workspace alive across calls pays the memset once. */
+ * (the log-sum-exp / row-term operand blocks the kernel's extra MMA k-step reads) and dq_ws fp32 [batch*seq*heads*64]
+ * (zeroed by the call, accumulated with red.global.add, converted into dqkv at the end). */
 int devias_flash_attn_fwd(const void* qkv, void* out, float* lse2, int batch, int seq, int heads, int head_dim, float scale,
                           void* stream);
 int devias_flash_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse2, void* dqkv, void* aug_ws,
-                          float* dq_ws, int dq_ws_is_zero, int batch, int seq, int heads, int head_dim, float scale, void* stream);
+                          float* dq_ws, int batch, int seq, int heads, int head_dim, float scale, void* stream);
 
 /* ---- streaming slot attention (folded form; devias_b200/slot_attention.py) ----------------------------
  * One pass over the context tokens of every clip, replacing per layer: LayerNorm(context) + to_k + to_v + q k^T + slot-axis

@@ -1,9 +1,10 @@
 """numpy restatement of the reference's FAME mask pipeline (TEST INFRASTRUCTURE; utils/transform/fame.py:29-110).
 
-PARITY UNPINNED against kornia: the reference delegates Gaussian blur and RGB->HSV to kornia, which is not installed here
-(no network), so the reference module itself cannot be imported.  This file restates those two published definitions
-independently of devias_b200/fame.py (scipy.ndimage for the blur, the textbook piecewise hue formula) and follows the
-reference line by line for everything else; tests/test_fame.py compares the two implementations."""
+The reference delegates Gaussian blur and RGB->HSV to kornia, which is not installed here (no network), so the reference module
+itself cannot be imported: parity against kornia's OUTPUTS is unpinned.  This file restates those two published definitions
+independently of devias_b200/fame.py (scipy.ndimage for the blur, the textbook piecewise hue formula), is pinned together with the
+product on hand-computed known answers of the definitions (tests/golden/fame_known_answers.json, sources stated there), and
+follows the reference line by line for everything else; tests/test_fame.py compares the two implementations."""
 import numpy as np
 from scipy import ndimage
 
