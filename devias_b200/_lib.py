@@ -43,6 +43,7 @@ _SIGS = {
     'devias_flash_attn_fwd': (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_float, _P]),
     'devias_flash_attn_bwd': (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, _P]),
     'devias_slot_stream_fwd': (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, _P]),
+    'devias_slot_stream_fwd_bf16': (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, _P]),
     'devias_slot_stream_bwd': (c_int, [_P] * 11 + [c_int] + [_P] * 3 + [c_int, c_int, c_int, c_int, _P]),
     'devias_layernorm_fwd': (c_int, [_P, _P, _P, _P, c_int, _P, _P, c_int, c_int, c_float, _P]),
     'devias_layernorm_bwd': (c_int, [_P, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),

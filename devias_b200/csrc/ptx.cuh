@@ -60,10 +60,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // Release builds spin on try_wait (which itself suspends the thread for a hardware-defined time slice); -DDV_DEBUG_SPIN
 // bounds the spin so that a protocol bug traps (-> cudaErrorLaunchFailure at the next sync) instead of hanging the GPU box.
 #ifdef DV_DEBUG_SPIN
+#ifndef DV_DEBUG_SPIN_BITS
+#define DV_DEBUG_SPIN_BITS 26
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) {
+    if (++spins > (1u << DV_DEBUG_SPIN_BITS)) {
       printf("devias_b200: mbarrier timeout block %d thread %d bar %u parity %u\n", blockIdx.x, threadIdx.x, smem_u32(bar), parity);
       __trap();
     }

@@ -266,9 +266,12 @@ def flash_attn_bwd(qkv, out, dout, lse2, B: int, N: int, H: int):
 
 
 def slot_stream_fwd(tokens, g, G, c0, want_attn=True, want_stats=True, eps=1e-5):
-    """tokens fp32 [B,N,768]; g [B,HS,768]; G,c0 [B,HS] -> U [B,HS,768], m, A [B,HS], attn [B,HS,N]|None, mu, rstd [B,N]|None"""
+    """tokens fp32 or bf16 [B,N,768]; g [B,HS,768]; G,c0 [B,HS] -> U [B,HS,768], m, A [B,HS], attn [B,HS,N]|None, mu, rstd [B,N]|None
+    (fp32 tokens: the fp32 streaming kernels of csrc/slot_attn.cu; bf16 tokens: the tcgen05 kernel of csrc/slot_attn_tc.cu)"""
     _need_cuda(tokens, g, G, c0)
-    assert tokens.dtype == torch.float32 and tokens.is_contiguous() and g.is_contiguous() and G.is_contiguous() and c0.is_contiguous()
+    assert tokens.dtype in (torch.float32, torch.bfloat16), 'slot_stream_fwd: tokens must be fp32 or bf16'
+    assert tokens.is_contiguous() and g.is_contiguous() and G.is_contiguous() and c0.is_contiguous()
+    assert g.dtype == torch.float32 and G.dtype == torch.float32 and c0.dtype == torch.float32
     B, N, D = tokens.shape
     HS = g.shape[1]
     dev = tokens.device
@@ -277,9 +280,9 @@ def slot_stream_fwd(tokens, g, G, c0, want_attn=True, want_stats=True, eps=1e-5)
     attn = torch.empty(B, HS, N, device=dev, dtype=torch.float32) if want_attn else None
     mu = torch.empty(B, N, device=dev, dtype=torch.float32) if want_stats else None
     rstd = torch.empty(B, N, device=dev, dtype=torch.float32) if want_stats else None
-    rc = _lib.lib().devias_slot_stream_fwd(tokens.data_ptr(), g.data_ptr(), G.data_ptr(), c0.data_ptr(), U.data_ptr(),
-                                           mA[0].data_ptr(), mA[1].data_ptr(), _ptr(attn), _ptr(mu), _ptr(rstd), B, N, D, HS // 4,
-                                           float(eps), _stream())
+    fn = _lib.lib().devias_slot_stream_fwd if tokens.dtype == torch.float32 else _lib.lib().devias_slot_stream_fwd_bf16
+    rc = fn(tokens.data_ptr(), g.data_ptr(), G.data_ptr(), c0.data_ptr(), U.data_ptr(), mA[0].data_ptr(), mA[1].data_ptr(),
+            _ptr(attn), _ptr(mu), _ptr(rstd), B, N, D, HS // 4, float(eps), _stream())
     _lib.check(rc, 'slot_stream_fwd')
     return U, mA[0], mA[1], attn, mu, rstd
 

@@ -98,6 +98,13 @@ int devias_slot_stream_fwd(const float* tokens, const float* g, const float* G, 
                            float* attn, float* mu, float* rstd, int batch, int n_tokens, int dim, int num_slots, float eps,
                            void* stream);
 
+/* Same contract for BF16 context tokens [batch, n_tokens, 768] (BASELINE config 5 "fp32 and bf16"): both contractions run on
+ * tcgen05 straight off the TMA-landed token tile (g and the softmax weights are rounded to bf16, accumulation in fp32, LayerNorm
+ * statistics / softmax in fp32); S in {2, 4, 8}.  Replaces agg_block/attention.py:32-40,120-141 when the model runs in bf16. */
+int devias_slot_stream_fwd_bf16(const void* tokens, const float* g, const float* G, const float* c0, float* U, float* m, float* A,
+                                float* attn, float* mu, float* rstd, int batch, int n_tokens, int dim, int num_slots, float eps,
+                                void* stream);
+
 /* Backward of devias_slot_stream_fwd.  attn / mu / rstd are the forward's outputs; dU, dm, dA (and optionally dattn) the
  * upstream gradients.  Writes dtokens [batch, n_tokens, 768] (accumulate_dtokens != 0: +=, used to sum the layers of the
  * aggregation block in place) and ACCUMULATES dg [batch, 4*S, 768], dG, dc0 [batch, 4*S].  S in {2, 4, 8} (S = 8 runs as two
