@@ -14,7 +14,8 @@
 // and the MN-major operand of phase 2 (rows = contraction index).  LayerNorm statistics of the tokens (the only per-element
 // work left on the CUDA cores: ~3 instructions per element) are taken from the tile by the four compute warps while the MMAs
 // of phase 1 run.  U accumulates in tensor memory over all tiles of a clip and is flushed with red.global.add per clip.
-// Warp roles: 0 = TMA producer, 1 = MMA issuer, 4-7 = g image / softmax (4, 5) / drain, 8-15 = LayerNorm statistics.
+// Warp roles: 0, 1, 4, 5 = slot-axis softmax (two heads each), 2 = TMA producer, 3 = MMA issuer, 4-7 = g image / drain,
+// 8-15 = LayerNorm statistics.
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -25,7 +26,7 @@ constexpr int kTT = 32;                             // tokens per tile
 constexpr int kTBoxes = kTD / 64;                   // 12 boxes of 64 bf16 channels (128 bytes)
 constexpr int kTBoxBytes = kTT * 128;               // 4 KiB
 constexpr int kTTileBytes = kTBoxes * kTBoxBytes;   // 48 KiB
-constexpr int kTcThreads = 512;                     // 16 warps: 0 = TMA producer, 1 = MMA issuer, 4-7 = slot warps, 8-15 = stats warps
+constexpr int kTcThreads = 512;                     // 16 warps, roles in the header comment
 constexpr int kTcStatSlots = 4;
 
 template <int HS>
@@ -148,10 +149,10 @@ slot_stream_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmTok, const SlotT
       prefetch_tmap(&tmTok);
       for (int s = 0; s < ST; ++s) { mbar_init(&full[s], 1); mbar_init(&tile_free[s], 9); }
       for (int s = 0; s < 2; ++s) {
-        mbar_init(&d1_full[s], 1); mbar_init(&d1_free[s], 2);
-        mbar_init(&w_full[s], 2); mbar_init(&w_free[s], 1);
+        mbar_init(&d1_full[s], 1); mbar_init(&d1_free[s], 4);
+        mbar_init(&w_full[s], 4); mbar_init(&w_free[s], 1);
       }
-      for (int s = 0; s < NS; ++s) { mbar_init(&st_full[s], 8); mbar_init(&st_free[s], 2); }
+      for (int s = 0; s < NS; ++s) { mbar_init(&st_full[s], 8); mbar_init(&st_free[s], 4); }
       mbar_init(d2_full, 1); mbar_init(d2_free, 4); mbar_init(g_ready, 1);
       fence_barrier_init();
     }
@@ -166,7 +167,7 @@ slot_stream_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmTok, const SlotT
   if (*tmem_slot != 0u) __trap();               // see TMEM_COLS
   pdl_wait();
 
-  if (warp == 0) {
+  if (warp == 2) {
     // =============================================================== TMA producer
     if (lane == 0) {
       for (int it = 0; it < n; ++it) {
@@ -177,7 +178,7 @@ slot_stream_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmTok, const SlotT
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
+  } else if (warp == 3) {
     // =============================================================== MMA issuer (whole warp converged, one elected lane issues)
     {
       const uint32_t lead = elect_one() ? 1u : 0u;
@@ -275,41 +276,48 @@ slot_stream_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmTok, const SlotT
       __syncwarp();
       if (lane == 0) mbar_arrive(&st_full[slot]);
     }
-  } else if (warp >= 4) {
-    // =============================================================== slot warps: g image, softmax (warps 4, 5), drain
-    const int tc = tid - 128, q = warp & 3;                                  // q: the TMEM lane quarter this warp may read
-    const bool sm_warp = q < 2;                                              // D1 (M = 64): token 16 q + lane, lanes 0..15
+  } else {
+    // =============================================================== softmax warps (0, 1: heads 0-1; 4, 5: heads 2-3) and slot warps
+    // (4-7: bf16 image of g, U out of tensor memory).  D1 (M = 64) keeps token 16 q + i in lane i < 16 of lane quarter q.
+    const int q = warp & 3;                                                  // the TMEM lane quarter this warp may read
+    const bool slot_warp = warp >= 4, sm_warp = q < 2;
+    const int tc = tid - 128;                                                // thread index among the slot warps
+    const int hg = warp >> 2;                                                // head group of a softmax warp
     const int tk = 16 * q + (lane & 15);
     const bool sm_thread = sm_warp && lane < 16;
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
-    float accA[HS], accM[HS];
+    constexpr int HH = HS / 2;                                               // (head, slot) rows per softmax thread
+    float accA[HH], accM[HH];
     int seg = 0;
     for (int it = 0; it < n;) {
       const int b = (start + it) / tpc;
       const int seg_n = min(n - it, tpc - (start + it) % tpc);               // tiles of this clip in our range
-      // ---- bf16 image of g[b]: [12 boxes][HSP rows][128 B], 16-byte chunks swizzled by (row & 7); rows >= HS are zero
-      for (int i = tc; i < HSP * 96; i += 128) {
-        const int row = i / 96, c8 = i - row * 96;
-        uint32_t w0 = 0u, w1 = 0u, w2 = 0u, w3 = 0u;
-        if (row < HS) {
-          const float4* src = reinterpret_cast<const float4*>(p.g + ((long long)b * HS + row) * kTD + 8 * c8);
-          const float4 x = __ldg(src), y = __ldg(src + 1);
-          w0 = pack_bf16(x.x, x.y); w1 = pack_bf16(x.z, x.w); w2 = pack_bf16(y.x, y.y); w3 = pack_bf16(y.z, y.w);
+      if (slot_warp) {
+        // ---- bf16 image of g[b]: [12 boxes][HSP rows][128 B], 16-byte chunks swizzled by (row & 7); rows >= HS are zero
+        for (int i = tc; i < HSP * 96; i += 128) {
+          const int row = i / 96, c8 = i - row * 96;
+          uint32_t w0 = 0u, w1 = 0u, w2 = 0u, w3 = 0u;
+          if (row < HS) {
+            const float4* src = reinterpret_cast<const float4*>(p.g + ((long long)b * HS + row) * kTD + 8 * c8);
+            const float4 x = __ldg(src), y = __ldg(src + 1);
+            w0 = pack_bf16(x.x, x.y); w1 = pack_bf16(x.z, x.w); w2 = pack_bf16(y.x, y.y); w3 = pack_bf16(y.z, y.w);
+          }
+          sts128(g_u + (c8 >> 3) * Cfg::G_BOX + row * 128 + (((c8 & 7) ^ (row & 7)) << 4), w0, w1, w2, w3);
         }
-        sts128(g_u + (c8 >> 3) * Cfg::G_BOX + row * 128 + (((c8 & 7) ^ (row & 7)) << 4), w0, w1, w2, w3);
+        if (tc < HS) { Gs[tc] = __ldg(p.G + b * HS + tc); c0s[tc] = __ldg(p.c0 + b * HS + tc); }
+        fence_proxy_async();
+        named_bar_sync(1, 128);
+        if (tc == 0) mbar_arrive(g_ready);
+      } else {
+        mbar_wait(g_ready, seg & 1);                                         // G / c0 of this clip are in shared memory
       }
-      if (tc < HS) { Gs[tc] = __ldg(p.G + b * HS + tc); c0s[tc] = __ldg(p.c0 + b * HS + tc); }
-#pragma unroll
-      for (int i = 0; i < HS; ++i) { accA[i] = 0.f; accM[i] = 0.f; }
-      fence_proxy_async();
-      named_bar_sync(1, 128);
-      if (tc == 0) mbar_arrive(g_ready);
-
       if (sm_warp) {
+#pragma unroll
+        for (int i = 0; i < HH; ++i) { accA[i] = 0.f; accM[i] = 0.f; }
         for (int e = it + seg_n, i2 = it; i2 < e; ++i2) {
           const int buf = i2 & 1, slot = i2 % NS;
           const int tok_base = ((start + i2) % tpc) * kTT;
-          // ---- softmax over the slots of each head, thread <-> token
+          // ---- softmax over the slots of each head, thread <-> (token, two heads)
           mbar_wait(&d1_full[buf], (i2 >> 1) & 1);
           tc_fence_after();
           uint32_t d[HSP];
@@ -326,13 +334,15 @@ slot_stream_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmTok, const SlotT
             const bool valid = tok < p.N;
             const uint32_t wt = w_u + buf * Cfg::W_BYTES + (tk & 7) * 2;
 #pragma unroll
-            for (int h = 0; h < 4; ++h) {
+            for (int hl = 0; hl < 2; ++hl) {
               float a[S];
               float mx = -INFINITY;
 #pragma unroll
               for (int s = 0; s < S; ++s) {
-                const int i = h * S + s;
-                a[s] = fmaf(r, __uint_as_float(d[i]) - mu * Gs[i], c0s[i]);
+                // (d is indexed with compile-time constants on both head groups so that it stays in registers)
+                const float dv_ = __uint_as_float(hg == 0 ? d[hl * S + s] : d[HH + hl * S + s]);
+                const int i = hg * HH + hl * S + s;
+                a[s] = fmaf(r, dv_ - mu * Gs[i], c0s[i]);
                 mx = fmaxf(mx, a[s]);
               }
               float sum = 0.f;
@@ -341,12 +351,12 @@ slot_stream_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmTok, const SlotT
               const float inv = valid ? 1.0f / sum : 0.f;
 #pragma unroll
               for (int s = 0; s < S; ++s) {
-                const int i = h * S + s;
+                const int il = hl * S + s, i = hg * HH + il;
                 const float av = a[s] * inv, w = av * r;
-                const __nv_bfloat16 wb = __float2bfloat16_rn(valid ? w : 0.f);
+                const __nv_bfloat16 wb = __float2bfloat16_rn(w);
                 sts16(wt + i * 128 + (((tk >> 3) ^ (i & 7)) << 4), *reinterpret_cast<const uint16_t*>(&wb));
-                accA[i] += av;
-                accM[i] = fmaf(valid ? w : 0.f, mu, accM[i]);
+                accA[il] += av;
+                accM[il] = fmaf(w, mu, accM[il]);
                 if (valid && p.attn != nullptr) p.attn[((long long)b * HS + i) * p.N + tok] = av;
               }
             }
@@ -357,21 +367,21 @@ slot_stream_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmTok, const SlotT
         }
         // ---- A / m of the clip segment
 #pragma unroll
-        for (int i = 0; i < HS; ++i) {
-          float a = sm_thread ? accA[i] : 0.f, mm = sm_thread ? accM[i] : 0.f;
+        for (int il = 0; il < HH; ++il) {
+          float a = sm_thread ? accA[il] : 0.f, mm = sm_thread ? accM[il] : 0.f;
 #pragma unroll
           for (int o = 1; o < 16; o <<= 1) {
             a += __shfl_xor_sync(0xffffffffu, a, o);
             mm += __shfl_xor_sync(0xffffffffu, mm, o);
           }
-          if (lane == 0) { atomicAdd(p.A + b * HS + i, a); atomicAdd(p.m + b * HS + i, mm); }
+          if (lane == 0) { atomicAdd(p.A + b * HS + hg * HH + il, a); atomicAdd(p.m + b * HS + hg * HH + il, mm); }
         }
       }
       it += seg_n;
-      // ---- U of the segment out of tensor memory
-      mbar_wait(d2_full, seg & 1);
-      tc_fence_after();
-      {
+      if (slot_warp) {
+        // ---- U of the segment out of tensor memory
+        mbar_wait(d2_full, seg & 1);
+        tc_fence_after();
         float* dst = p.U + (long long)b * HS * kTD + 32 * q + lane;
 #pragma unroll 1
         for (int mb = 0; mb < 6; ++mb) {
@@ -381,10 +391,10 @@ slot_stream_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmTok, const SlotT
 #pragma unroll
           for (int i = 0; i < HS; ++i) red_add_f32(dst + i * kTD + 128 * mb, __uint_as_float(u[i]));
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(d2_free);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(d2_free);
       ++seg;
     }
   }

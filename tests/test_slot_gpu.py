@@ -65,3 +65,35 @@ def test_slot_stream_bwd(B, N, S, with_dattn):
     acc = base.clone()
     ops.slot_stream_bwd(tok, mu, rstd, g, G, attn, dU, dm, dA, dattn, dtokens=acc)
     assert_close(acc, base.double() + rdt, 2e-5, 'accumulated d tokens')
+
+
+@pytest.mark.parametrize('B,N,S', [(1, 32, 2), (2, 1568, 2), (3, 100, 4), (1, 1569, 2), (2, 1568, 4), (2, 1568, 8), (3, 100, 8),
+                                   (40, 1568, 2)])
+def test_slot_stream_fwd_bf16_tokens(B, N, S):
+    """BF16 context tokens (BASELINE config 5 'fp32 and bf16'): the tcgen05 kernel of csrc/slot_attn_tc.cu against the float64
+    evaluation of the folded contract (agg_block/attention.py:32-40,120-141) on the SAME bf16 token values.  LayerNorm statistics
+    are fp32-exact (1e-5); the logits see g rounded to bf16 -- against a reference that rounds g the same way the slot-axis softmax
+    agrees to 1e-5, i.e. the tensor-core contraction itself is exact up to fp32 accumulation; against the unrounded reference
+    the outputs carry bf16 operand rounding (tolerance 5e-3, inside the 1e-2 bf16 budget of BASELINE.json north_star)."""
+    from devias_b200 import ops, slot_attention as SA
+    HS = 4 * S
+    gen = torch.Generator(device='cuda').manual_seed(11 * S + B)
+    tok = (torch.randn(B, N, 768, device='cuda', generator=gen) * (1.0 + torch.rand(B, N, 1, device='cuda', generator=gen))
+           + 0.25).to(torch.bfloat16)
+    g = torch.randn(B, HS, 768, device='cuda', generator=gen) * 0.05
+    G = g.sum(-1).contiguous()
+    c0 = torch.randn(B, HS, device='cuda', generator=gen) * 0.3
+    U, m, A, attn, mu, rstd = ops.slot_stream_fwd(tok, g, G, c0)
+    t64 = tok.double()
+    rmu = t64.mean(-1)
+    rr = torch.rsqrt((t64 - rmu.unsqueeze(-1)).square().mean(-1) + 1e-5)
+    rU, rm, rA, ra = SA.slot_stream_torch(t64, rmu, rr, g.double(), G.double(), c0.double())
+    _, _, _, ra_b = SA.slot_stream_torch(t64, rmu, rr, g.to(torch.bfloat16).double(), G.double(), c0.double())
+    assert_close(mu, rmu, 1e-5, 'mu')
+    assert_close(rstd, rr, 1e-5, 'rstd')
+    assert_close(attn, ra_b, 1e-5, 'attn vs reference with bf16-rounded g')
+    assert_close(attn, ra, 5e-3, 'attn')
+    assert_close(A, rA, 5e-3, 'A')
+    assert_close(m, rm, 5e-3, 'm')
+    assert_close(U, rU, 5e-3, 'U')
+    assert torch.allclose(attn.view(B, 4, S, N).sum(2), torch.ones(B, 4, N, device='cuda'), atol=1e-5)
