@@ -284,10 +284,10 @@ slot_stream_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmTok, const SlotT
     const int tc = tid - 128;                                                // thread index among the slot warps
     const int hg = warp >> 2;                                                // head group of a softmax warp
     const int tk = 16 * q + (lane & 15);
-    const bool sm_thread = sm_warp && lane < 16;
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
-    constexpr int HH = HS / 2;                                               // (head, slot) rows per softmax thread
-    float accA[HH], accM[HH];
+    constexpr int HH = HS / 2;                                               // (head, slot) rows per softmax warp
+    const int hl = lane >> 4;                                                // lanes 0-15: first head of the group, 16-31: second
+    float accA[S], accM[S];
     int seg = 0;
     for (int it = 0; it < n;) {
       const int b = (start + it) / tpc;
@@ -312,12 +312,15 @@ slot_stream_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmTok, const SlotT
         mbar_wait(g_ready, seg & 1);                                         // G / c0 of this clip are in shared memory
       }
       if (sm_warp) {
+        const int row0 = hg * HH + hl * S;                                   // this thread's (head, slot) rows: row0 .. row0 + S - 1
+        float Gr[S], cr[S];
 #pragma unroll
-        for (int i = 0; i < HH; ++i) { accA[i] = 0.f; accM[i] = 0.f; }
+        for (int s = 0; s < S; ++s) { accA[s] = 0.f; accM[s] = 0.f; Gr[s] = Gs[row0 + s]; cr[s] = c0s[row0 + s]; }
         for (int e = it + seg_n, i2 = it; i2 < e; ++i2) {
           const int buf = i2 & 1, slot = i2 % NS;
-          const int tok_base = ((start + i2) % tpc) * kTT;
-          // ---- softmax over the slots of each head, thread <-> (token, two heads)
+          const int tok = ((start + i2) % tpc) * kTT + tk;
+          // ---- softmax over the slots of one head, thread <-> (token, head): TMEM lane i < 16 holds token 16 q + i; lanes 16-31
+          //      take the group's second head of the same tokens through a shuffle
           mbar_wait(&d1_full[buf], (i2 >> 1) & 1);
           tc_fence_after();
           uint32_t d[HSP];
@@ -326,55 +329,53 @@ slot_stream_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmTok, const SlotT
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&d1_free[buf]);
+          float a[S];
+#pragma unroll
+          for (int s = 0; s < S; ++s) {
+            // (d is indexed with compile-time constants on both head groups so that it stays in registers)
+            const uint32_t lo = hg == 0 ? d[s] : d[HH + s], hi = hg == 0 ? d[S + s] : d[HH + S + s];
+            const uint32_t other = __shfl_sync(0xffffffffu, hi, lane & 15);
+            a[s] = __uint_as_float(hl == 0 ? lo : other);
+          }
           mbar_wait(&st_full[slot], (i2 / NS) & 1);
+          const float mu = stat[(slot * kTT + tk) * 2], r = stat[(slot * kTT + tk) * 2 + 1];
+          const bool valid = tok < p.N;
+          float mx = -INFINITY;
+#pragma unroll
+          for (int s = 0; s < S; ++s) {
+            a[s] = fmaf(r, a[s] - mu * Gr[s], cr[s]);
+            mx = fmaxf(mx, a[s]);
+          }
+          float sum = 0.f;
+#pragma unroll
+          for (int s = 0; s < S; ++s) { a[s] = expf(a[s] - mx); sum += a[s]; }
+          const float inv = valid ? 1.0f / sum : 0.f;
           mbar_wait(&w_free[buf], ((i2 >> 1) & 1) ^ 1);
-          if (sm_thread) {
-            const float mu = stat[(slot * kTT + tk) * 2], r = stat[(slot * kTT + tk) * 2 + 1];
-            const int tok = tok_base + tk;
-            const bool valid = tok < p.N;
-            const uint32_t wt = w_u + buf * Cfg::W_BYTES + (tk & 7) * 2;
+          const uint32_t wt = w_u + buf * Cfg::W_BYTES + (tk & 7) * 2;
 #pragma unroll
-            for (int hl = 0; hl < 2; ++hl) {
-              float a[S];
-              float mx = -INFINITY;
-#pragma unroll
-              for (int s = 0; s < S; ++s) {
-                // (d is indexed with compile-time constants on both head groups so that it stays in registers)
-                const float dv_ = __uint_as_float(hg == 0 ? d[hl * S + s] : d[HH + hl * S + s]);
-                const int i = hg * HH + hl * S + s;
-                a[s] = fmaf(r, dv_ - mu * Gs[i], c0s[i]);
-                mx = fmaxf(mx, a[s]);
-              }
-              float sum = 0.f;
-#pragma unroll
-              for (int s = 0; s < S; ++s) { a[s] = expf(a[s] - mx); sum += a[s]; }
-              const float inv = valid ? 1.0f / sum : 0.f;
-#pragma unroll
-              for (int s = 0; s < S; ++s) {
-                const int il = hl * S + s, i = hg * HH + il;
-                const float av = a[s] * inv, w = av * r;
-                const __nv_bfloat16 wb = __float2bfloat16_rn(w);
-                sts16(wt + i * 128 + (((tk >> 3) ^ (i & 7)) << 4), *reinterpret_cast<const uint16_t*>(&wb));
-                accA[il] += av;
-                accM[il] = fmaf(w, mu, accM[il]);
-                if (valid && p.attn != nullptr) p.attn[((long long)b * HS + i) * p.N + tok] = av;
-              }
-            }
+          for (int s = 0; s < S; ++s) {
+            const int i = row0 + s;
+            const float av = a[s] * inv, w = av * r;
+            const __nv_bfloat16 wb = __float2bfloat16_rn(w);
+            sts16(wt + i * 128 + (((tk >> 3) ^ (i & 7)) << 4), *reinterpret_cast<const uint16_t*>(&wb));
+            accA[s] += av;
+            accM[s] = fmaf(w, mu, accM[s]);
+            if (valid && p.attn != nullptr) p.attn[((long long)b * HS + i) * p.N + tok] = av;
           }
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) { mbar_arrive(&w_full[buf]); mbar_arrive(&st_free[slot]); }
         }
-        // ---- A / m of the clip segment
+        // ---- A / m of the clip segment: sums over the 16 tokens of each half warp
 #pragma unroll
-        for (int il = 0; il < HH; ++il) {
-          float a = sm_thread ? accA[il] : 0.f, mm = sm_thread ? accM[il] : 0.f;
+        for (int s = 0; s < S; ++s) {
+          float a = accA[s], mm = accM[s];
 #pragma unroll
           for (int o = 1; o < 16; o <<= 1) {
             a += __shfl_xor_sync(0xffffffffu, a, o);
             mm += __shfl_xor_sync(0xffffffffu, mm, o);
           }
-          if (lane == 0) { atomicAdd(p.A + b * HS + hg * HH + il, a); atomicAdd(p.m + b * HS + hg * HH + il, mm); }
+          if ((lane & 15) == 0) { atomicAdd(p.A + b * HS + row0 + s, a); atomicAdd(p.m + b * HS + row0 + s, mm); }
         }
       }
       it += seg_n;
