@@ -185,8 +185,11 @@ slot_stream_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmTok, const SlotT
       constexpr uint32_t idesc1 = umma_idesc_bf16(64, HSP, false, false);    // D1[tokens x HSP]: A = tile K-major, B = g K-major
       constexpr uint32_t idesc2 = umma_idesc_bf16(128, HSP, true, false);    // D2[channels x HSP]: A = tile MN-major, B = w K-major
       int seg1 = 0, seg2 = 0;                                                // clip segments begun by phase 1 / finished by phase 2
-      auto phase2 = [&](int it) {
-        const int gt = start + it, st = it % ST, buf = it & 1;
+      // stage / buffer indices are passed as values that are compile-time constants after unrolling (see the loop below): the
+      // operand descriptors are then shared-memory base + constant, which the compiler keeps in uniform registers (descriptors
+      // built from a run-time stage index live in vector registers and cost two R2UR + their latency per MMA)
+      auto phase2 = [&](int it, int st, int buf) {
+        const int gt = start + it;
         const bool first = it == 0 || gt % tpc == 0, last = it == n - 1 || (gt + 1) % tpc == 0;
         mbar_wait(&w_full[buf], (it >> 1) & 1);
         if (first) mbar_wait(d2_free, (seg2 & 1) ^ 1);                       // U of the previous segment has left tensor memory
@@ -204,8 +207,7 @@ slot_stream_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmTok, const SlotT
         umma_commit_lead(lead, &w_free[buf]);
         if (last) { umma_commit_lead(lead, d2_full); ++seg2; }
       };
-      auto phase1 = [&](int it) {
-        const int st = it % ST, buf = it & 1;
+      auto phase1 = [&](int it, int st, int buf) {
         mbar_wait(&full[st], (it / ST) & 1);
         mbar_wait(&d1_free[buf], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
@@ -221,19 +223,29 @@ slot_stream_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmTok, const SlotT
         }
         umma_commit_lead(lead, &d1_full[buf]);
       };
-      for (int it = 0; it < n; ++it) {
-        const bool first = it == 0 || (start + it) % tpc == 0;
-        if (first) {
-          if (it > 0) phase2(it - 1);            // finish the previous clip before waiting for the next clip's g
-          mbar_wait(g_ready, seg1 & 1);
-          ++seg1;
-          phase1(it);
-        } else {
-          phase1(it);
-          phase2(it - 1);
+      constexpr int UF = (ST % 2 == 0) ? ST : 2 * ST;                        // unroll: stage and buffer index periodic in it
+      for (int base = 0; base < n; base += UF) {
+#pragma unroll
+        for (int j = 0; j < UF; ++j) {
+          const int it = base + j;
+          if (it < n) {
+            const int pst = ((j + UF - 1) % UF) % ST, pbuf = (j + UF - 1) & 1;   // of tile it - 1
+            const bool first = it == 0 || (start + it) % tpc == 0;
+            if (first) {
+              if (it > 0) phase2(it - 1, pst, pbuf);   // finish the previous clip before waiting for the next clip's g
+              mbar_wait(g_ready, seg1 & 1);
+              ++seg1;
+              phase1(it, j % ST, j & 1);
+            } else {
+              phase1(it, j % ST, j & 1);
+              phase2(it - 1, pst, pbuf);
+            }
+          }
         }
       }
-      phase2(n - 1);
+#pragma unroll
+      for (int j = 0; j < UF; ++j)
+        if ((n - 1) % UF == j) phase2(n - 1, j % ST, j & 1);
     }
     __syncwarp();
   } else if (warp >= 8) {
