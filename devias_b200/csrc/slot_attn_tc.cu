@@ -14,8 +14,8 @@
 // and the MN-major operand of phase 2 (rows = contraction index).  LayerNorm statistics of the tokens (the only per-element
 // work left on the CUDA cores: ~3 instructions per element) are taken from the tile by the four compute warps while the MMAs
 // of phase 1 run.  U accumulates in tensor memory over all tiles of a clip and is flushed with red.global.add per clip.
-// Warp roles: 0, 1, 4, 5 = slot-axis softmax (two heads each), 2 = TMA producer, 3 = MMA issuer, 4-7 = g image / drain,
-// 8-15 = LayerNorm statistics.
+// Warp roles: 0, 1, 4, 5 = slot-axis softmax (two heads each), 2 = TMA producer, 3 / 16 = MMA issuers (phase 1 / phase 2),
+// 4-7 = g image / drain, 8-15 = LayerNorm statistics.
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -26,7 +26,7 @@ constexpr int kTT = 32;                             // tokens per tile
 constexpr int kTBoxes = kTD / 64;                   // 12 boxes of 64 bf16 channels (128 bytes)
 constexpr int kTBoxBytes = kTT * 128;               // 4 KiB
 constexpr int kTTileBytes = kTBoxes * kTBoxBytes;   // 48 KiB
-constexpr int kTcThreads = 512;                     // 16 warps, roles in the header comment
+constexpr int kTcThreads = 544;                     // 16 warps, roles in the header comment
 constexpr int kTcStatSlots = 4;
 
 template <int HS>
@@ -178,8 +178,8 @@ slot_stream_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmTok, const SlotT
       }
     }
     __syncwarp();
-  } else if (warp == 3) {
-    // =============================================================== MMA issuer (whole warp converged, one elected lane issues)
+  } else if (warp == 3 || warp == 16) {
+    // =============================================================== MMA issuers (whole warp converged, one elected lane issues)
     {
       const uint32_t lead = elect_one() ? 1u : 0u;
       constexpr uint32_t idesc1 = umma_idesc_bf16(64, HSP, false, false);    // D1[tokens x HSP]: A = tile K-major, B = g K-major
@@ -224,31 +224,32 @@ slot_stream_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmTok, const SlotT
         umma_commit_lead(lead, &d1_full[buf]);
       };
       constexpr int UF = (ST % 2 == 0) ? ST : 2 * ST;                        // unroll: stage and buffer index periodic in it
-      for (int base = 0; base < n; base += UF) {
+      // Two issuing warps: warp 3 queues the logits MMAs of a tile as soon as it has landed, warp 16 the weighted-sum MMAs as soon
+      // as the softmax weights exist.  (One thread issuing both had to wait for softmax(it - 1) before it could queue phase 1 of
+      // tile it + 1: the token ring ran dry behind that serialisation.)
+      if (warp == 3) {
+        for (int base = 0; base < n; base += UF) {
 #pragma unroll
-        for (int j = 0; j < UF; ++j) {
-          const int it = base + j;
-          if (it < n) {
-            const int pst = ((j + UF - 1) % UF) % ST, pbuf = (j + UF - 1) & 1;   // of tile it - 1
-            const bool first = it == 0 || (start + it) % tpc == 0;
-            if (first) {
-              if (it > 0) phase2(it - 1, pst, pbuf);   // finish the previous clip before waiting for the next clip's g
-              mbar_wait(g_ready, seg1 & 1);
-              ++seg1;
+          for (int j = 0; j < UF; ++j) {
+            const int it = base + j;
+            if (it < n) {
+              if (it == 0 || (start + it) % tpc == 0) { mbar_wait(g_ready, seg1 & 1); ++seg1; }
               phase1(it, j % ST, j & 1);
-            } else {
-              phase1(it, j % ST, j & 1);
-              phase2(it - 1, pst, pbuf);
             }
           }
         }
-      }
+      } else {
+        for (int base = 0; base < n; base += UF) {
 #pragma unroll
-      for (int j = 0; j < UF; ++j)
-        if ((n - 1) % UF == j) phase2(n - 1, j % ST, j & 1);
+          for (int j = 0; j < UF; ++j) {
+            const int it = base + j;
+            if (it < n) phase2(it, j % ST, j & 1);
+          }
+        }
+      }
     }
     __syncwarp();
-  } else if (warp >= 8) {
+  } else if (warp >= 8 && warp < 16) {
     // =============================================================== stats warps: LayerNorm moments of the tokens, one tile ahead
     const int tl = (warp - 8) * 4 + (lane >> 3), pq = lane & 7;              // 8 threads per token, one 16-byte unit per box each
     for (int it = 0; it < n; ++it) {
