@@ -328,7 +328,7 @@ slot_stream_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmTok, const SlotT
         const int row0 = hg * HH + hl * S;                                   // this thread's (head, slot) rows: row0 .. row0 + S - 1
         float Gr[S], cr[S];
 #pragma unroll
-        for (int s = 0; s < S; ++s) { accA[s] = 0.f; accM[s] = 0.f; Gr[s] = Gs[row0 + s]; cr[s] = c0s[row0 + s]; }
+        for (int s = 0; s < S; ++s) { accA[s] = 0.f; accM[s] = 0.f; Gr[s] = Gs[row0 + s]; cr[s] = c0s[row0 + s] * 1.4426950408889634f; }
         for (int e = it + seg_n, i2 = it; i2 < e; ++i2) {
           const int buf = i2 & 1, slot = i2 % NS;
           const int tok = ((start + i2) % tpc) * kTT + tk;
@@ -354,15 +354,16 @@ slot_stream_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmTok, const SlotT
           const float mu = stat[(slot * kTT + tk) * 2], r = stat[(slot * kTT + tk) * 2 + 1];
           const bool valid = tok < p.N;
           float mx = -INFINITY;
+          const float r2 = r * 1.4426950408889634f;                          // logits in the log2 domain: one MUFU.EX2 per weight
 #pragma unroll
           for (int s = 0; s < S; ++s) {
-            a[s] = fmaf(r, a[s] - mu * Gr[s], cr[s]);
+            a[s] = fmaf(r2, a[s] - mu * Gr[s], cr[s]);
             mx = fmaxf(mx, a[s]);
           }
           float sum = 0.f;
 #pragma unroll
-          for (int s = 0; s < S; ++s) { a[s] = expf(a[s] - mx); sum += a[s]; }
-          const float inv = valid ? 1.0f / sum : 0.f;
+          for (int s = 0; s < S; ++s) { a[s] = fast_exp2(a[s] - mx); sum += a[s]; }
+          const float inv = valid ? __frcp_rn(sum) : 0.f;
           mbar_wait(&w_free[buf], ((i2 >> 1) & 1) ^ 1);
           const uint32_t wt = w_u + buf * Cfg::W_BYTES + (tk & 7) * 2;
 #pragma unroll
