@@ -49,6 +49,7 @@ _SIGS = {
     'devias_layernorm_bwd': (c_int, [_P, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),
     'devias_colsum_bf16': (c_int, [_P, c_int64, c_int, c_int, _P, _P]),
     'devias_cast_f32_bf16': (c_int, [_P, _P, c_int64, _P]),
+    'devias_cast_bf16_f32': (c_int, [_P, _P, c_int64, _P]),
     'devias_scale_rows_cast': (c_int, [_P, _P, c_int, c_int, _P, c_int, _P]),
     'devias_patch_embed_fwd': (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     'devias_patchify': (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P]),

@@ -99,7 +99,9 @@ class AggregationBlock(nn.Module):
                 h = slot_linear.linear(slot_linear.layer_norm(x, cross_ff.norm), net[0].weight, net[0].bias)
                 x = slot_linear.linear(net[1](h), net[3].weight, net[3].bias) + x
             last = self.last_layer[0]
-            return (slot_linear.layer_norm(x, last) if isinstance(last, nn.LayerNorm) else last(x)), sim
+            out = slot_linear.layer_norm(x, last) if isinstance(last, nn.LayerNorm) else last(x)
+            # the reference carries the slots in the context's dtype (agg_block/agg_block.py:128 `.type_as(data)`)
+            return (out if data.dtype == torch.float32 else out.to(data.dtype)), sim
 
     def forward(self, data):
         b, *axis = data.shape    # as in the reference (agg_block/agg_block.py:121-122) the channel dim counts as an axis

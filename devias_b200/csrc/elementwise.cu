@@ -88,7 +88,38 @@ __global__ void __launch_bounds__(256) patchify_kernel(const T* __restrict__ cli
   }
 }
 
+
+// bf16 -> fp32, 8 elements per thread (the fp32 slot-attention backward consumes an upcast copy of bf16 tokens)
+__global__ void __launch_bounds__(256) cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out,
+                                                            long long n8, long long n) {
+  pdl_trigger();
+  pdl_wait();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 v = *reinterpret_cast<const uint4*>(in + i * 8);
+    const float2 a = unpack_bf16(v.x), b = unpack_bf16(v.y), c = unpack_bf16(v.z), d = unpack_bf16(v.w);
+    *reinterpret_cast<float4*>(out + i * 8) = make_float4(a.x, a.y, b.x, b.y);
+    *reinterpret_cast<float4*>(out + i * 8 + 4) = make_float4(c.x, c.y, d.x, d.y);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (long long i = n8 * 8; i < n; ++i) out[i] = __bfloat162float(in[i]);
+}
+
 }  // namespace dv
+
+extern "C" int devias_cast_bf16_f32(const void* in, float* out, int64_t n, void* stream) {
+  using namespace dv;
+  DV_REQUIRE(in && out, "null pointer");
+  DV_REQUIRE((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "16-byte alignment");
+  if (n <= 0) return DEVIAS_OK;
+  const long long n8 = n / 8;
+  long long blocks = (n8 + 255) / 256;
+  if (blocks > sm_count() * 16) blocks = sm_count() * 16;
+  if (blocks < 1) blocks = 1;
+  DV_CHECK_CUDA(launch_k(cast_bf16_f32_kernel, dim3((unsigned)((int)blocks)), dim3((unsigned)(256)), (size_t)(0), static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(in), out, n8, (long long)n));
+  DV_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return DEVIAS_OK;
+}
 
 extern "C" int devias_cast_f32_bf16(const float* in, void* out, int64_t n, void* stream) {
   using namespace dv;

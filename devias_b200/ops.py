@@ -126,6 +126,16 @@ def cast_bf16(src: torch.Tensor, dst: Optional[torch.Tensor] = None):
     return dst
 
 
+def cast_f32(src: torch.Tensor):
+    """bf16 -> fp32 copy"""
+    _need_cuda(src)
+    assert src.dtype == torch.bfloat16 and src.is_contiguous()
+    dst = torch.empty(src.shape, device=src.device, dtype=torch.float32)
+    rc = _lib.lib().devias_cast_bf16_f32(src.data_ptr(), dst.data_ptr(), src.numel(), _stream())
+    _lib.check(rc, 'cast_bf16_f32')
+    return dst
+
+
 def scale_rows_cast(src: torch.Tensor, row_scale: torch.Tensor, rows_per_scale: int):
     _need_cuda(src, row_scale)
     assert src.dtype == torch.float32 and src.is_contiguous()
@@ -287,15 +297,21 @@ def slot_stream_fwd(tokens, g, G, c0, want_attn=True, want_stats=True, eps=1e-5)
     return U, mA[0], mA[1], attn, mu, rstd
 
 
+SLOT_BF16_TOKENS = True     # bf16 context tokens: forward on the tcgen05 kernel (csrc/slot_attn_tc.cu)
+
+
 def slot_stream_bwd(tokens, mu, rstd, g, G, attn, dU, dm, dA, dattn=None, dtokens=None):
-    """-> (dtokens, dg, dG, dc0); when `dtokens` is given the token gradient is accumulated into it in place"""
+    """-> (dtokens fp32, dg, dG, dc0); when `dtokens` is given the token gradient is accumulated into it in place.
+    bf16 tokens: the fp32 backward kernels run on an upcast copy (the token gradient stays fp32)."""
     _need_cuda(tokens, g, dU)
+    if tokens.dtype == torch.bfloat16:
+        tokens = cast_f32(tokens.contiguous())
     B, N, D = tokens.shape
     HS = g.shape[1]
     dev = tokens.device
     acc = dtokens is not None
     if dtokens is None:
-        dtokens = torch.empty_like(tokens)
+        dtokens = torch.empty(tokens.shape, device=dev, dtype=torch.float32)
     dg = torch.zeros(B, HS, D, device=dev, dtype=torch.float32)
     dGc = torch.zeros(2, B, HS, device=dev, dtype=torch.float32)
     cont = lambda t: None if t is None else t.contiguous()

@@ -48,8 +48,12 @@ class SlotStreamFn(torch.autograd.Function):
             out_dt = None
             if sink.pending == 0:
                 out_dt, sink.buf = sink.buf, None
+                if tokens.dtype == torch.bfloat16:
+                    out_dt = ops.cast_bf16(out_dt)
             return out_dt, dg, dG, dc0, None
         dt, dg, dG, dc0 = ops.slot_stream_bwd(tokens, mu, rstd, g, G, attn, dU, dm, dA, dattn)
+        if need_dt and tokens.dtype == torch.bfloat16:
+            dt = ops.cast_bf16(dt)
         return (dt if need_dt else None), dg, dG, dc0, None
 
 
@@ -58,6 +62,7 @@ def new_sink():
 
 
 def slot_stream(tokens, mu, r, g, G, c0, sink=None):
-    if tokens.dtype != torch.float32:
-        tokens = tokens.float()
+    """fp32 tokens: the fp32 streaming kernels (1e-5 contract); bf16 tokens: the tcgen05 kernel (bf16 operand rounding)"""
+    if tokens.dtype not in (torch.float32, torch.bfloat16):
+        raise TypeError(f'devias_b200 slot attention takes fp32 or bf16 context tokens, got {tokens.dtype}')
     return SlotStreamFn.apply(tokens, g, G, c0, sink)

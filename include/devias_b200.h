@@ -142,6 +142,8 @@ int devias_colsum_bf16(const void* a, int64_t lda, int rows, int cols, float* ou
  * Conv3d(k=s=(2,16,16)) (model/modeling_slot.py:167-176) becomes devias_gemm_bf16 with the RESID_F32 epilogue adding the
  * bias and the sin-cos table (:354-355).  row = t*196 + h*14 + w, col = c*512 + dt*256 + dy*16 + dx. */
 int devias_cast_f32_bf16(const float* in, void* out, int64_t n, void* stream);
+/* bf16 -> fp32 (tokens handed to the fp32 slot-attention backward when the context arrives in bf16) */
+int devias_cast_bf16_f32(const void* in, float* out, int64_t n, void* stream);
 /* Tube patch embedding as an implicit GEMM (model/modeling_slot.py:167-177 Conv3d(k = s = (2,16,16)) + flatten/transpose, bias, and
  * the position table of :354-355 in the epilogue): out fp32 [B*1568, 768] = im2col(clip) W^T + bias + pos[token % 1568].
  * The A operand is fetched by a 5-D TMA box straight from the NCTHW fp32 clip [B, 3, 16, 224, 224] (no patch matrix, no

@@ -67,6 +67,41 @@ def test_agg_block_gradients_fp32():
         assert_close(p.grad, ref, 5e-5, 'grad ' + k)
 
 
+@pytest.mark.parametrize('S,d,tied', [(2, 3, True), (4, 2, False), (8, 2, True)])
+def test_agg_block_bf16_tokens_vs_oracle(S, d, tied):
+    """bf16 context tokens through the module interface (BASELINE config 5 'fp32 and bf16'): forward on the tcgen05 streaming
+    kernel, backward on the fp32 kernels over an upcast copy; checked against the fp32 oracle of agg_block/agg_block.py:121-139
+    evaluated on the same bf16 token values.  Tolerance 1e-2 (bf16 budget of BASELINE.json north_star); slots come back in bf16
+    as in the reference (`.type_as(data)`, agg_block/agg_block.py:128)."""
+    from devias_b200.agg_block import AggregationBlock
+    B = 2
+    sd = MG.agg_state(S, d, tied, seed=13)
+    m = _quiet(AggregationBlock, num_latents=S, weight_tie_layers=tied, depth=d).cuda()
+    m.load_state_dict(sd)
+    xb = O.synth_tokens(B, seed=8).to(torch.bfloat16)
+    ws, wa = MG.probe_weights([(B, S, 768), (B * 4, S, 1568)], seed=6)
+    xc = xb.cuda().requires_grad_(True)
+    slots, sim = m(xc)
+    assert slots.dtype == torch.bfloat16 and sim.dtype == torch.float32
+    ((slots.float() * ws.cuda()).sum() + (sim * wa.cuda()).sum()).backward()
+    osd = {'agg_block.' + k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    xo = xb.float().requires_grad_(True)
+    oslots, osim = O.aggregation_block(osd, xo)
+    ((oslots * ws).sum() + (osim * wa).sum()).backward()
+    assert_close(slots.float(), oslots, 1e-2, 'slots')
+    assert_close(sim, osim, 1e-2, 'sim')
+    assert xc.grad.dtype == torch.bfloat16
+    assert_close(xc.grad.float(), xo.grad, 2e-2, 'd tokens')
+    scale = max(float(v.grad.norm()) for v in osd.values() if v.grad is not None)
+    for k, p in m.named_parameters():
+        ref = osd['agg_block.' + k].grad
+        if tied and k.startswith('layers.0.'):      # the oracle's state dict holds one leaf per layer: a tied weight's gradient is their sum
+            ref = sum(osd['agg_block.layers.%d.%s' % (l, k[len('layers.0.'):])].grad for l in range(d))
+        if float(ref.norm()) < 1e-3 * scale:
+            continue
+        assert_close(p.grad, ref, 3e-2, 'grad ' + k)
+
+
 @pytest.mark.parametrize('name,depth,S,d,tied,C,B', MG.MODEL_CASES)
 def test_student_forward_bf16_vs_golden(name, depth, S, d, tied, C, B):
     from devias_b200.modeling_slot import VisionTransformer, slot_vit_base_patch16_224
