@@ -45,6 +45,7 @@ _SIGS = {
     'devias_slot_stream_fwd': (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, _P]),
     'devias_slot_stream_fwd_bf16': (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, _P]),
     'devias_slot_stream_bwd': (c_int, [_P] * 11 + [c_int] + [_P] * 3 + [c_int, c_int, c_int, c_int, _P]),
+    'devias_slot_stream_bwd_bf16': (c_int, [_P] * 11 + [c_int] + [_P] * 3 + [c_int, c_int, c_int, c_int, _P]),
     'devias_layernorm_fwd': (c_int, [_P, _P, _P, _P, c_int, _P, _P, c_int, c_int, c_float, _P]),
     'devias_layernorm_bwd': (c_int, [_P, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),
     'devias_colsum_bf16': (c_int, [_P, c_int64, c_int, c_int, _P, _P]),

@@ -302,10 +302,9 @@ SLOT_BF16_TOKENS = True     # bf16 context tokens: forward on the tcgen05 kernel
 
 def slot_stream_bwd(tokens, mu, rstd, g, G, attn, dU, dm, dA, dattn=None, dtokens=None):
     """-> (dtokens fp32, dg, dG, dc0); when `dtokens` is given the token gradient is accumulated into it in place.
-    bf16 tokens: the fp32 backward kernels run on an upcast copy (the token gradient stays fp32)."""
+    bf16 tokens: the tcgen05 backward of csrc/slot_attn_tc_bwd.cu (the token gradient stays fp32)."""
     _need_cuda(tokens, g, dU)
-    if tokens.dtype == torch.bfloat16:
-        tokens = cast_f32(tokens.contiguous())
+    assert tokens.dtype in (torch.float32, torch.bfloat16) and tokens.is_contiguous()
     B, N, D = tokens.shape
     HS = g.shape[1]
     dev = tokens.device
@@ -316,9 +315,9 @@ def slot_stream_bwd(tokens, mu, rstd, g, G, attn, dU, dm, dA, dattn=None, dtoken
     dGc = torch.zeros(2, B, HS, device=dev, dtype=torch.float32)
     cont = lambda t: None if t is None else t.contiguous()
     dU, dm, dA, dattn = cont(dU), cont(dm), cont(dA), cont(dattn)
-    rc = _lib.lib().devias_slot_stream_bwd(tokens.data_ptr(), mu.data_ptr(), rstd.data_ptr(), g.data_ptr(), G.data_ptr(),
-                                           attn.data_ptr(), dU.data_ptr(), dm.data_ptr(), dA.data_ptr(), _ptr(dattn),
-                                           dtokens.data_ptr(), int(acc), dg.data_ptr(), dGc[0].data_ptr(), dGc[1].data_ptr(),
-                                           B, N, D, HS // 4, _stream())
+    fn = _lib.lib().devias_slot_stream_bwd if tokens.dtype == torch.float32 else _lib.lib().devias_slot_stream_bwd_bf16
+    rc = fn(tokens.data_ptr(), mu.data_ptr(), rstd.data_ptr(), g.data_ptr(), G.data_ptr(), attn.data_ptr(), dU.data_ptr(),
+            dm.data_ptr(), dA.data_ptr(), _ptr(dattn), dtokens.data_ptr(), int(acc), dg.data_ptr(), dGc[0].data_ptr(),
+            dGc[1].data_ptr(), B, N, D, HS // 4, _stream())
     _lib.check(rc, 'slot_stream_bwd')
     return dtokens, dg, dGc[0], dGc[1]

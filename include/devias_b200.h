@@ -114,6 +114,14 @@ int devias_slot_stream_bwd(const float* tokens, const float* mu, const float* rs
                            float* dtokens, int accumulate_dtokens, float* dg, float* dG, float* dc0, int batch, int n_tokens,
                            int dim, int num_slots, void* stream);
 
+/* Backward of devias_slot_stream_fwd_bf16 (same arguments as devias_slot_stream_bwd with BF16 tokens): the three contractions
+ * (dots with [g; dU], dg, dtokens) run on tcgen05 off the token tile and one bf16 image of [g; dU]; per-token coefficient math,
+ * accumulation and the token gradient [batch, n_tokens, 768] stay fp32. */
+int devias_slot_stream_bwd_bf16(const void* tokens, const float* mu, const float* rstd, const float* g, const float* G,
+                                const float* attn, const float* dU, const float* dm, const float* dA, const float* dattn,
+                                float* dtokens, int accumulate_dtokens, float* dg, float* dG, float* dc0, int batch,
+                                int n_tokens, int dim, int num_slots, void* stream);
+
 /* dtype ids for entry points that accept several input element types */
 #define DEVIAS_DTYPE_F32 0
 #define DEVIAS_DTYPE_BF16 1
