@@ -637,8 +637,13 @@ def main():
             out.update(extras)
             grid = [g for g in extras['slot_grid'] if g.get('S') == cfg['num_latents'] and g.get('batch') == 256 and 'fwd_gbs' in g]
             if grid and 'roofline' in out:
-                out['roofline']['slot_attention']['microbench'] = grid[0]
-                out['roofline']['slot_attention']['microbench_frac_of_hbm'] = grid[0]['fwd_frac']
+                f32 = [g for g in grid if g.get('tokens') == 'f32'] or grid
+                b16 = [g for g in grid if g.get('tokens') == 'bf16']
+                out['roofline']['slot_attention']['microbench'] = f32[0]          # fp32 token stream (what the model feeds, 1e-5 contract)
+                out['roofline']['slot_attention']['microbench_frac_of_hbm'] = f32[0]['fwd_frac']
+                if b16:                                                            # bf16 token stream: the tcgen05 kernels
+                    out['roofline']['slot_attention']['microbench_bf16'] = b16[0]
+                    out['roofline']['slot_attention']['microbench_bf16_frac_of_hbm'] = b16[0]['fwd_frac']
         if world == 1 and not args.no_cpu_baseline:
             stepf, cores = cpu_reference_step_fn(cfg)
             stepf()

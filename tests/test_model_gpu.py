@@ -70,7 +70,7 @@ def test_agg_block_gradients_fp32():
 @pytest.mark.parametrize('S,d,tied', [(2, 3, True), (4, 2, False), (8, 2, True)])
 def test_agg_block_bf16_tokens_vs_oracle(S, d, tied):
     """bf16 context tokens through the module interface (BASELINE config 5 'fp32 and bf16'): forward on the tcgen05 streaming
-    kernel, backward on the fp32 kernels over an upcast copy; checked against the fp32 oracle of agg_block/agg_block.py:121-139
+    kernel, backward on its tcgen05 counterpart (csrc/slot_attn_tc_bwd.cu); checked against the fp32 oracle of agg_block/agg_block.py:121-139
     evaluated on the same bf16 token values.  Tolerance 1e-2 (bf16 budget of BASELINE.json north_star); slots come back in bf16
     as in the reference (`.type_as(data)`, agg_block/agg_block.py:128)."""
     from devias_b200.agg_block import AggregationBlock

@@ -97,3 +97,41 @@ def test_slot_stream_fwd_bf16_tokens(B, N, S):
     assert_close(m, rm, 5e-3, 'm')
     assert_close(U, rU, 5e-3, 'U')
     assert torch.allclose(attn.view(B, 4, S, N).sum(2), torch.ones(B, 4, N, device='cuda'), atol=1e-5)
+
+
+@pytest.mark.parametrize('B,N,S,with_dattn', [(1, 32, 2, True), (2, 1568, 2, True), (3, 100, 4, False), (1, 1569, 2, False),
+                                               (2, 1568, 4, True), (2, 1568, 8, True), (3, 100, 8, False), (40, 1568, 2, False)])
+def test_slot_stream_bwd_bf16_tokens(B, N, S, with_dattn):
+    """tcgen05 backward for bf16 tokens (csrc/slot_attn_tc_bwd.cu) vs float64 autograd of the folded contract on the same bf16
+    token values.  g, dU and the per-token coefficients enter the MMAs as bf16, accumulation and the coefficient math are fp32:
+    tolerance 1e-2 (bf16 budget of BASELINE.json north_star; measured 2-3e-3)."""
+    from devias_b200 import ops, slot_attention as SA
+    HS = 4 * S
+    gen = torch.Generator(device='cuda').manual_seed(17 + S + B)
+    tok = (torch.randn(B, N, 768, device='cuda', generator=gen) * (1.0 + torch.rand(B, N, 1, device='cuda', generator=gen))
+           + 0.25).to(torch.bfloat16)
+    g = torch.randn(B, HS, 768, device='cuda', generator=gen) * 0.05
+    G = g.sum(-1).contiguous()
+    c0 = torch.randn(B, HS, device='cuda', generator=gen) * 0.3
+    dU = torch.randn(B, HS, 768, device='cuda', generator=gen)
+    dm = torch.randn(B, HS, device='cuda', generator=gen)
+    dA = torch.randn(B, HS, device='cuda', generator=gen)
+    dattn = torch.randn(B, HS, N, device='cuda', generator=gen) if with_dattn else None
+    U, m, A, attn, mu, rstd = ops.slot_stream_fwd(tok, g, G, c0)
+    dt, dg, dG, dc0 = ops.slot_stream_bwd(tok, mu, rstd, g, G, attn, dU, dm, dA, dattn)
+    assert dt.dtype == torch.float32
+    leaves = [t.double().requires_grad_(True) for t in (tok, g, G, c0)]
+    t64 = leaves[0]
+    rmu = t64.mean(-1)
+    rr = torch.rsqrt((t64 - rmu.unsqueeze(-1)).square().mean(-1) + 1e-5)
+    outs = SA.slot_stream_torch(t64, rmu, rr, leaves[1], leaves[2], leaves[3])
+    go = [dU.double(), dm.double(), dA.double(), (dattn.double() if with_dattn else torch.zeros_like(outs[3]))]
+    rdt, rdg, rdG, rdc0 = torch.autograd.grad(outs, leaves, go)
+    assert_close(dt, rdt, 1e-2, 'd tokens')
+    assert_close(dg, rdg, 1e-2, 'dg')
+    assert_close(dG, rdG, 1e-2, 'dG')
+    assert_close(dc0, rdc0, 1e-2, 'dc0')
+    base = torch.randn(B, N, 768, device='cuda', generator=gen)
+    acc = base.clone()
+    ops.slot_stream_bwd(tok, mu, rstd, g, G, attn, dU, dm, dA, dattn, dtokens=acc)
+    assert_close(acc - base, rdt, 1e-2, 'accumulated d tokens')
