@@ -60,6 +60,7 @@ def parse():
     ap.add_argument('--no-extras', action='store_true', help='skip slot grid / eval sweep / gpu reference (N=1 extras)')
     ap.add_argument('--torch-adamw', action='store_true', help='torch fused AdamW instead of the arena optimizer pass')
     ap.add_argument('--no-graph', action='store_true', help='eager launches instead of the captured CUDA graph')
+    ap.add_argument('--token-dtype', default='f32', choices=['f32', 'bf16'], help='dtype of the encoder tokens handed to the slot block (bf16: the tcgen05 slot kernels)')
     return ap.parse_args()
 
 
@@ -225,6 +226,8 @@ def measure_train(name, cfg, args, dev, world, rank, with_roofline=True, with_e2
     model.load_state_dict(O.synth_state_dict(num_classes=C, num_latents=cfg['num_latents'], agg_depth=cfg['agg_depth'],
                                              agg_weights_tie=cfg['agg_weights_tie'], depth=12, seed=3))
     model = model.to(dev).train()
+    if args.token_dtype == 'bf16':
+        model.token_dtype = torch.bfloat16
     gate = parity_gate(model, cfg, dev)
     crit = TrainLoss(torch.nn.CrossEntropyLoss(), 'KL', C)
     decay = [p for n_, p in model.named_parameters() if p.dim() > 1 and n_ not in model.no_weight_decay()]

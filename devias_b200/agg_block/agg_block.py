@@ -30,6 +30,7 @@ class AggregationBlock(nn.Module):
         self.first_order = first_order
         self.depth = depth
         self.weight_tie_layers = weight_tie_layers
+        self.slot_dtype = None      # None: slots come back in the context's dtype (reference behaviour); the student model pins fp32
         self._fast_ok = (pos_enc_type == 'none' and pre_norm and not post_norm and activation == 'gelu'
                          and attn_dropout == 0. and ff_dropout == 0. and not more_dropout)
 
@@ -101,7 +102,8 @@ class AggregationBlock(nn.Module):
             last = self.last_layer[0]
             out = slot_linear.layer_norm(x, last) if isinstance(last, nn.LayerNorm) else last(x)
             # the reference carries the slots in the context's dtype (agg_block/agg_block.py:128 `.type_as(data)`)
-            return (out if data.dtype == torch.float32 else out.to(data.dtype)), sim
+            want = data.dtype if self.slot_dtype is None else self.slot_dtype
+            return (out if out.dtype == want else out.to(want)), sim
 
     def forward(self, data):
         b, *axis = data.shape    # as in the reference (agg_block/agg_block.py:121-122) the channel dim counts as an axis

@@ -311,6 +311,8 @@ class VisionTransformer(nn.Module):
         self._arena = None
         self._pos_dev = None
         #: dtype of the encoder tokens handed to the aggregation block (fp32 keeps the slot path at fp32 accuracy)
+        # dtype of the encoder tokens handed to the aggregation block: fp32 (default; the fp32 streaming slot kernels, 1e-5
+        # contract) or bf16 (what the reference's K/V projections see under autocast; the tcgen05 slot kernels).  Slots stay fp32.
         self.token_dtype = torch.float32
 
     def _init_weights(self, m):
@@ -417,6 +419,7 @@ class VisionTransformer(nn.Module):
 
     def forward(self, x, return_attn=False):
         x = self.forward_features(x, return_attn)
+        self.agg_block.slot_dtype = torch.float32
         slots, attn = self.agg_block(x)
         with torch.autocast('cuda', enabled=False):
             if self.slot_matching_method == 'hard_select':
