@@ -13,7 +13,8 @@ from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, 'csrc')
-LIB_PATH = os.path.join(CSRC, 'libdevias_b200.so')
+# DEVIAS_B200_LIB: developer switch for A/B builds of the same sources (e.g. -DDV_DEBUG_SPIN); default = the in-tree library
+LIB_PATH = os.environ.get('DEVIAS_B200_LIB') or os.path.join(CSRC, 'libdevias_b200.so')
 
 _lib = None
 

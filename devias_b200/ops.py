@@ -285,8 +285,9 @@ def slot_stream_fwd(tokens, g, G, c0, want_attn=True, want_stats=True, eps=1e-5)
     B, N, D = tokens.shape
     HS = g.shape[1]
     dev = tokens.device
-    U = torch.zeros(B, HS, D, device=dev, dtype=torch.float32)
-    mA = torch.zeros(2, B, HS, device=dev, dtype=torch.float32)
+    acc = torch.zeros(B * HS * (D + 2), device=dev, dtype=torch.float32)      # U | m | A accumulate (+=): one zero-fill
+    U = acc[:B * HS * D].view(B, HS, D)
+    mA = acc[B * HS * D:].view(2, B, HS)
     attn = torch.empty(B, HS, N, device=dev, dtype=torch.float32) if want_attn else None
     mu = torch.empty(B, N, device=dev, dtype=torch.float32) if want_stats else None
     rstd = torch.empty(B, N, device=dev, dtype=torch.float32) if want_stats else None

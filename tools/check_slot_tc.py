@@ -1,5 +1,5 @@
 """Diagnostic for the tcgen05 bf16-token slot-attention kernel (csrc/slot_attn_tc.cu): per-output errors against the float64
-evaluation of the folded contract on the SAME bf16 tokens, and timings.  DEVIAS_DEBUG_LIB=<path> loads a -DDV_DEBUG_SPIN build
+evaluation of the folded contract on the SAME bf16 tokens, and timings.  DEVIAS_B200_LIB=<path> loads a -DDV_DEBUG_SPIN build
 (a protocol bug then traps instead of hanging the box).  Usage: python tools/check_slot_tc.py [--time]"""
 import os
 import sys
@@ -7,11 +7,7 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from devias_b200 import _lib  # noqa: E402
-
-if os.environ.get('DEVIAS_DEBUG_LIB'):
-    _lib.LIB_PATH = os.environ['DEVIAS_DEBUG_LIB']
-from devias_b200 import ops, slot_attention as SA  # noqa: E402
+from devias_b200 import _lib, ops, slot_attention as SA  # noqa: E402
 
 
 def rel(a, b):
