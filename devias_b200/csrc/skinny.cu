@@ -230,13 +230,22 @@ __global__ void __launch_bounds__(256) skinny_outer_kernel(const float* __restri
 
 // ------------------------------------------------------------------------------------------------------- many rows (M > 32)
 // K400 training has 64 slot rows per GPU, an evaluation batch of 256 has 512: there the products stop being weight-read bound
-// and the row-tile-at-a-time kernels above re-read the weights per 16 rows.  Classic register-tiled fp32 SIMT GEMM instead:
-// CTA tile 64 x 64, 256 threads x (4 x 4) outputs, k-chunks of 16 staged in shared memory as [l][i] / [l][j] so that the inner
-// loop is 16 FMAs per two 16-byte shared loads; split over the contraction (atomics) where the output has too few tiles.
+// and the row-tile-at-a-time kernels above re-read the weights per 16 rows.  Register-tiled fp32 SIMT GEMM instead:
 //   MODE 0 (nt)   : C[i, j] = sum_l x[i, l] w[j, l]        i = row m (mapped), j = n          both operands contiguous along l
 //   MODE 1 (nn)   : C[i, j] += sum_l x[i, l] w[l, j]                                        B contiguous along j
 //   MODE 2 (outer): C[i, j] (+)= sum_l a[l, i] b[l, j]     l = row m (mapped)               both operands contiguous along i / j
-constexpr int kTg = 64, kTgK = 16, kTgPad = 4;
+// k-chunks staged in shared memory as [l][i] / [l][j], the next chunk's 16-byte loads in flight while the current one is
+// multiplied, split over the contraction where the output has too few tiles (partial sums leave through
+// red.global.add.v4.f32: a quarter of the L2 atomic operations of scalar atomics).  Two shapes of the same template, chosen
+// per mode by measurement at 64 rows (a product is 0.2-0.3 GFLOP, i.e. ~4 us of the whole GPU's FFMA rate: latency and the
+// shared-memory return path decide, not the FMA pipe):
+//   R = 1: CTA tile 64 x 64, 256 threads x (4 x 4) outputs, chunks of 32.  Many small CTAs: best where the contraction is short
+//          (weight gradients: 64 rows) or the output narrow (input gradients).
+//   R = 2: CTA tile 64 x 128, 128 threads x (8 x 8) outputs, chunks of 16.  The shared-memory -> register return path (128 B per
+//          clock and SM; an LDS.128 costs four of its cycles even when the lanes read the same 16 bytes) carries 2 bytes per FMA
+//          with 4 x 4 outputs per thread -- twice the FFMA time, ncu: 3.3 of 4 warps per scheduler waiting on shared loads --
+//          and 1 byte with 8 x 8.  Forward products (nt, both operands stored transposed): 22 -> 16 us at 768 -> 3072.
+constexpr int kTgI = 64, kTgPad = 4, kTgSplitK = 32;   // rows per CTA tile; split granularity of the contraction
 
 struct TileArgs {
   const float* A; const float* B; float* C;
@@ -244,7 +253,7 @@ struct TileArgs {
   long long a_batch, b_batch, c_batch;
   int I, J, L;                       // output rows, output columns, contraction length
   int ldb, ldc;                      // MODE 0: w row stride (= K); MODE 1: w row stride (= N); MODE 2: c row stride (= J)
-  int l_per_split;
+  int l_per_split;                   // a multiple of kTgSplitK
   int accumulate;                    // MODE 2: c += ; (MODE 0 / 1 always add atomically onto a pre-filled output)
   float* colsum; long long colsum_batch;   // MODE 2: colsum[i] (+)= sum_l a[l, i]
 };
@@ -258,110 +267,160 @@ __device__ __forceinline__ float4 ld4_guard(const float* p, int valid, bool vec)
   if (valid > 3) v.w = __ldg(p + 3);
   return v;
 }
+__device__ __forceinline__ bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-template <int MODE>
-__global__ void __launch_bounds__(256) tile_gemm_kernel(const TileArgs p, int splits) {
+template <int R>
+struct TileShape {
+  static constexpr int NT = 256 / R;         // threads: (16 / R) x 16
+  static constexpr int TJ = 64 * R;          // columns per CTA tile
+  static constexpr int KC = 32 / R;          // contraction chunk
+  static constexpr int PA = 2, PB = 2 * R;   // 16-byte pieces per thread and chunk of the A / B operand
+};
+
+template <int MODE, int R>
+__global__ void __launch_bounds__(TileShape<R>::NT, R == 1 ? 4 : 3) tile_gemm_kernel(const TileArgs p, int splits) {
+  using T = TileShape<R>;
+  constexpr int NT = T::NT, TJ = T::TJ, KC = T::KC, PA = T::PA, PB = T::PB, MR = 4 * R;   // MR x MR outputs per thread
   pdl_trigger();
   pdl_wait();
-  __shared__ float As[kTgK][kTg + kTgPad];
-  __shared__ float Bs[kTgK][kTg + kTgPad];
+  __shared__ __align__(16) float As[KC][kTgI + kTgPad];
+  __shared__ __align__(16) float Bs[KC][TJ + kTgPad];
   const int tid = threadIdx.x;
   const int z = blockIdx.z / splits, split = blockIdx.z % splits;
-  const int i0 = blockIdx.y * kTg, j0 = blockIdx.x * kTg;
+  const int i0 = blockIdx.y * kTgI, j0 = blockIdx.x * TJ;
   const int l_begin = split * p.l_per_split, l_end = min(p.L, l_begin + p.l_per_split);
-  const int ti = tid >> 4, tj = tid & 15;            // 16 x 16 threads, each 4 x 4 outputs
-  float acc[4][4];
+  if (l_begin >= l_end) return;                       // (the launchers size the split count so that this does not happen)
+  // thread (ti, tj): rows {(64 / R) ra + 4 ti + a}, columns {64 rb + 4 tj + b}   (ra, rb < R;  a, b < 4)
+  const int ti = tid >> 4, tj = tid & 15;
+  float acc[MR][MR];
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
+  for (int a = 0; a < MR; ++a)
 #pragma unroll
-    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+    for (int b = 0; b < MR; ++b) acc[a][b] = 0.f;
 
-  // loader roles
-  //  "along l": thread -> (row r = tid / 4 of the 64, l4 = (tid % 4) * 4): one 16-byte load, stored transposed
-  //  "along i/j": thread -> (l = tid / 16, c4 = (tid % 16) * 4): one 16-byte load, stored as is
-  const int lr = tid >> 2, ll4 = (tid & 3) * 4;
-  const int sl = tid >> 4, sc4 = (tid & 15) * 4;
-  const float* a_row = nullptr; const float* b_row = nullptr;
-  bool a_vec = false, b_vec = false;
-  if (MODE == 0 || MODE == 1) {
-    const bool ok = i0 + lr < p.I;
-    a_row = ok ? p.A + p.am.off(i0 + lr, z) : nullptr;
-    a_vec = ok && ((reinterpret_cast<uintptr_t>(a_row) & 15) == 0);
+  // loader roles: the chunk of an operand is (rows x KC) floats = 16-byte pieces idx = tid + NT q
+  //  "along l" (operand rows contiguous in l): row = idx / (KC / 4), l4 = (idx % (KC / 4)) * 4  (NT q keeps l4), stored transposed
+  //  "along i/j" (operand contiguous across its rows): l = idx / (W / 4), c4 = (idx % (W / 4)) * 4  (W = 64 / TJ), stored as is
+  constexpr int LQ = KC / 4;
+  const int ll4 = (tid % LQ) * 4;
+  const float* a_row[PA];
+  const float* b_row[PB];
+#pragma unroll
+  for (int q = 0; q < PA; ++q) {
+    const int r = i0 + (tid + NT * q) / LQ;
+    a_row[q] = ((MODE == 0 || MODE == 1) && r < p.I) ? p.A + p.am.off(r, z) : nullptr;
   }
-  if (MODE == 0) {
-    const bool ok = j0 + lr < p.J;
-    b_row = ok ? p.B + (long long)z * p.b_batch + (long long)(j0 + lr) * p.ldb : nullptr;
-    b_vec = ok && ((reinterpret_cast<uintptr_t>(b_row) & 15) == 0);
+#pragma unroll
+  for (int q = 0; q < PB; ++q) {
+    const int r = j0 + (tid + NT * q) / LQ;
+    b_row[q] = (MODE == 0 && r < p.J) ? p.B + (long long)z * p.b_batch + (long long)r * p.ldb : nullptr;
   }
   float csum = 0.f;                                   // MODE 2: column sums of a (thread tid < 64 <-> i = i0 + tid)
-  auto fetch = [&](int l0, float4& av, float4& bv) {  // this thread's 16 bytes of the A and B chunk starting at l0
-    av = make_float4(0.f, 0.f, 0.f, 0.f);
-    bv = av;
-    if (MODE == 0 || MODE == 1) {
-      if (a_row != nullptr) av = ld4_guard(a_row + l0 + ll4, l_end - (l0 + ll4), a_vec && ((l0 + ll4) & 3) == 0);
-    } else {
-      const int l = l0 + sl;
-      if (l < l_end) {
-        const float* src = p.A + p.am.off(l, z) + i0 + sc4;
-        av = ld4_guard(src, p.I - (i0 + sc4), (reinterpret_cast<uintptr_t>(src) & 15) == 0);
+  auto fetch = [&](int l0, float4 (&av)[PA], float4 (&bv)[PB]) {   // this thread's pieces of the A and B chunk starting at l0
+#pragma unroll
+    for (int q = 0; q < PA; ++q) {
+      av[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (MODE == 0 || MODE == 1) {
+        const float* src = a_row[q] + l0 + ll4;
+        if (a_row[q] != nullptr) av[q] = ld4_guard(src, l_end - (l0 + ll4), al16(src));
+      } else {
+        const int idx = tid + NT * q, l = l0 + idx / (kTgI / 4), c4 = (idx % (kTgI / 4)) * 4;
+        if (l < l_end) {
+          const float* src = p.A + p.am.off(l, z) + i0 + c4;
+          av[q] = ld4_guard(src, p.I - (i0 + c4), al16(src));
+        }
       }
     }
-    if (MODE == 0) {
-      if (b_row != nullptr) bv = ld4_guard(b_row + l0 + ll4, l_end - (l0 + ll4), b_vec && ((l0 + ll4) & 3) == 0);
-    } else {
-      const int l = l0 + sl;
-      if (l < l_end) {
-        const float* src = (MODE == 1 ? p.B + (long long)z * p.b_batch + (long long)l * p.ldb : p.B + p.bm.off(l, z)) + j0 + sc4;
-        bv = ld4_guard(src, p.J - (j0 + sc4), (reinterpret_cast<uintptr_t>(src) & 15) == 0);
+#pragma unroll
+    for (int q = 0; q < PB; ++q) {
+      bv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (MODE == 0) {
+        const float* src = b_row[q] + l0 + ll4;
+        if (b_row[q] != nullptr) bv[q] = ld4_guard(src, l_end - (l0 + ll4), al16(src));
+      } else {
+        const int idx = tid + NT * q, l = l0 + idx / (TJ / 4), c4 = (idx % (TJ / 4)) * 4;
+        if (l < l_end) {
+          const float* src = (MODE == 1 ? p.B + (long long)z * p.b_batch + (long long)l * p.ldb : p.B + p.bm.off(l, z)) + j0 + c4;
+          bv[q] = ld4_guard(src, p.J - (j0 + c4), al16(src));
+        }
       }
     }
   };
-  float4 av, bv;
-  if (l_begin < l_end) fetch(l_begin, av, bv);
-  for (int l0 = l_begin; l0 < l_end; l0 += kTgK) {
+  float4 av[PA], bv[PB];
+  fetch(l_begin, av, bv);
+  for (int l0 = l_begin; l0 < l_end; l0 += KC) {
     __syncthreads();                                  // the previous chunk has been consumed
-    if (MODE == 0 || MODE == 1) {
-      As[ll4][lr] = av.x; As[ll4 + 1][lr] = av.y; As[ll4 + 2][lr] = av.z; As[ll4 + 3][lr] = av.w;
-    } else {
-      *reinterpret_cast<float4*>(&As[sl][sc4]) = av;
+#pragma unroll
+    for (int q = 0; q < PA; ++q) {
+      const int idx = tid + NT * q;
+      if (MODE == 0 || MODE == 1) {
+        const int r = idx / LQ;
+        As[ll4][r] = av[q].x; As[ll4 + 1][r] = av[q].y; As[ll4 + 2][r] = av[q].z; As[ll4 + 3][r] = av[q].w;
+      } else {
+        *reinterpret_cast<float4*>(&As[idx / (kTgI / 4)][(idx % (kTgI / 4)) * 4]) = av[q];
+      }
     }
-    if (MODE == 0) {
-      Bs[ll4][lr] = bv.x; Bs[ll4 + 1][lr] = bv.y; Bs[ll4 + 2][lr] = bv.z; Bs[ll4 + 3][lr] = bv.w;
-    } else {
-      *reinterpret_cast<float4*>(&Bs[sl][sc4]) = bv;
+#pragma unroll
+    for (int q = 0; q < PB; ++q) {
+      const int idx = tid + NT * q;
+      if (MODE == 0) {
+        const int r = idx / LQ;
+        Bs[ll4][r] = bv[q].x; Bs[ll4 + 1][r] = bv[q].y; Bs[ll4 + 2][r] = bv[q].z; Bs[ll4 + 3][r] = bv[q].w;
+      } else {
+        *reinterpret_cast<float4*>(&Bs[idx / (TJ / 4)][(idx % (TJ / 4)) * 4]) = bv[q];
+      }
     }
     __syncthreads();
-    if (l0 + kTgK < l_end) fetch(l0 + kTgK, av, bv);  // next chunk in flight while this one is multiplied
+    if (l0 + KC < l_end) fetch(l0 + KC, av, bv);      // next chunk in flight while this one is multiplied
 #pragma unroll
-    for (int l = 0; l < kTgK; ++l) {
-      const float4 a4 = *reinterpret_cast<const float4*>(&As[l][ti * 4]);
-      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[l][tj * 4]);
-      const float aa[4] = {a4.x, a4.y, a4.z, a4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
+    for (int l = 0; l < KC; ++l) {
+      float aa[MR], bb[MR];
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
+      for (int r = 0; r < R; ++r) {
+        const float4 a4 = *reinterpret_cast<const float4*>(&As[l][(kTgI / R) * r + ti * 4]);
+        const float4 b4 = *reinterpret_cast<const float4*>(&Bs[l][64 * r + tj * 4]);
+        aa[4 * r] = a4.x; aa[4 * r + 1] = a4.y; aa[4 * r + 2] = a4.z; aa[4 * r + 3] = a4.w;
+        bb[4 * r] = b4.x; bb[4 * r + 1] = b4.y; bb[4 * r + 2] = b4.z; bb[4 * r + 3] = b4.w;
+      }
 #pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(aa[a], bb[b], acc[a][b]);
+      for (int a = 0; a < MR; ++a)
+#pragma unroll
+        for (int b = 0; b < MR; ++b) acc[a][b] = fmaf(aa[a], bb[b], acc[a][b]);
     }
-    if (MODE == 2 && p.colsum != nullptr && blockIdx.x == 0 && tid < kTg) {
+    if (MODE == 2 && p.colsum != nullptr && blockIdx.x == 0 && tid < kTgI) {
 #pragma unroll
-      for (int l = 0; l < kTgK; ++l) csum += As[l][tid];
+      for (int l = 0; l < KC; ++l) csum += As[l][tid];
     }
   }
   // ---- output
 #pragma unroll
-  for (int a = 0; a < 4; ++a) {
-    const int i = i0 + ti * 4 + a;
+  for (int a = 0; a < MR; ++a) {
+    const int i = i0 + (a >> 2) * (kTgI / R) + ti * 4 + (a & 3);
     if (i >= p.I) continue;
     float* crow = (MODE == 2) ? p.C + (long long)z * p.c_batch + (long long)i * p.ldc : p.C + p.cm.off(i, z);
 #pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      const int j = j0 + tj * 4 + b;
-      if (j >= p.J) continue;
-      if (MODE == 2) crow[j] = p.accumulate ? crow[j] + acc[a][b] : acc[a][b];
-      else atomicAdd(crow + j, acc[a][b]);
+    for (int h = 0; h < R; ++h) {
+      const int jt = j0 + h * 64 + tj * 4;
+      const float* v = &acc[a][h * 4];
+      const bool vec = jt + 3 < p.J && al16(crow + jt);
+      if (MODE == 2 && !p.accumulate) {
+        if (vec) {
+          *reinterpret_cast<float4*>(crow + jt) = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+#pragma unroll
+          for (int b = 0; b < 4; ++b)
+            if (jt + b < p.J) crow[jt + b] = v[b];
+        }
+      } else if (vec) {                               // (MODE 2: each output belongs to one CTA, so the reduction is a plain += )
+        red_add_v4_f32(crow + jt, v[0], v[1], v[2], v[3]);
+      } else {
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+          if (jt + b < p.J) atomicAdd(crow + jt + b, v[b]);
+      }
     }
   }
-  if (MODE == 2 && p.colsum != nullptr && blockIdx.x == 0 && tid < kTg && i0 + tid < p.I) {
+  if (MODE == 2 && p.colsum != nullptr && blockIdx.x == 0 && tid < kTgI && i0 + tid < p.I) {
     float* d = p.colsum + (long long)z * p.colsum_batch + i0 + tid;
     *d = p.accumulate ? *d + csum : csum;
   }
@@ -384,11 +443,25 @@ static int skinny_max_rows() {       // up to here the weight-streaming kernels;
   return v;
 }
 
-static int tile_splits(int tiles, int L) {
-  int splits = (2 * sm_count() + tiles - 1) / tiles;          // ~2 CTAs per SM
-  const int max_splits = (L + 4 * kTgK - 1) / (4 * kTgK);     // at least 4 k-chunks per split
-  if (splits > max_splits) splits = max_splits;
-  return splits < 1 ? 1 : splits;
+// split of the contraction over CTAs: ~`per_sm` CTAs per SM, whole kTgSplitK pieces per split, no empty split
+static void tile_split(int tiles, int L, int per_sm, int* splits, int* l_per_split) {
+  const int chunks = (L + kTgSplitK - 1) / kTgSplitK;
+  int want = (per_sm * sm_count() + tiles - 1) / tiles;
+  if (want > chunks) want = chunks;
+  if (want < 1) want = 1;
+  const int per = (chunks + want - 1) / want;
+  *splits = (chunks + per - 1) / per;
+  *l_per_split = per * kTgSplitK;
+}
+
+template <int MODE, int R>
+static cudaError_t launch_tile(TileArgs& t, int batch, bool split, cudaStream_t stream) {
+  using T = TileShape<R>;
+  const int gx = (t.J + T::TJ - 1) / T::TJ, gy = (t.I + kTgI - 1) / kTgI;
+  int splits = 1;
+  t.l_per_split = (t.L + kTgSplitK - 1) / kTgSplitK * kTgSplitK;
+  if (split) tile_split(gx * gy * batch, t.L, R == 1 ? 2 : 3, &splits, &t.l_per_split);
+  return launch_k(tile_gemm_kernel<MODE, R>, dim3(gx, gy, batch * splits), dim3(T::NT), (size_t)0, stream, t, splits);
 }
 
 static RowMap make_map(const int64_t* m) {
@@ -412,14 +485,10 @@ extern "C" int devias_skinny_nt(const float* x, const int64_t* x_map, const floa
     TileArgs t{};
     t.A = x; t.B = w; t.C = y; t.am = make_map(x_map); t.cm = make_map(y_map); t.b_batch = w_batch;
     t.I = M; t.J = N; t.L = K; t.ldb = K;
-    const int tiles = ((M + kTg - 1) / kTg) * ((N + kTg - 1) / kTg) * batch;
-    const int splits = tile_splits(tiles, K);
-    t.l_per_split = ((K + splits - 1) / splits + kTgK - 1) / kTgK * kTgK;
     int fill_blocks = (M * N + 255) / 256;
     if (fill_blocks > 4 * sm_count()) fill_blocks = 4 * sm_count();
     DV_CHECK_CUDA(launch_k(rows_fill_kernel, dim3(fill_blocks, 1, batch), dim3(256), (size_t)0, (cudaStream_t)stream, y, t.cm, bias, M, N));
-    DV_CHECK_CUDA(launch_k(tile_gemm_kernel<0>, dim3((N + kTg - 1) / kTg, (M + kTg - 1) / kTg, batch * splits), dim3(256), (size_t)0,
-                           (cudaStream_t)stream, t, splits));
+    DV_CHECK_CUDA((launch_tile<0, 2>(t, batch, true, (cudaStream_t)stream)));
     count_launch(2);
     return DEVIAS_OK;
   }
@@ -448,11 +517,7 @@ extern "C" int devias_skinny_nn(const float* x, const int64_t* x_map, const floa
     TileArgs t{};
     t.A = x; t.B = w; t.C = y; t.am = make_map(x_map); t.cm = make_map(y_map); t.b_batch = w_batch;
     t.I = M; t.J = N; t.L = K; t.ldb = N;
-    const int tiles = ((M + kTg - 1) / kTg) * ((N + kTg - 1) / kTg) * batch;
-    const int splits = tile_splits(tiles, K);
-    t.l_per_split = ((K + splits - 1) / splits + kTgK - 1) / kTgK * kTgK;
-    DV_CHECK_CUDA(launch_k(tile_gemm_kernel<1>, dim3((N + kTg - 1) / kTg, (M + kTg - 1) / kTg, batch * splits), dim3(256), (size_t)0,
-                           (cudaStream_t)stream, t, splits));
+    DV_CHECK_CUDA((launch_tile<1, 1>(t, batch, true, (cudaStream_t)stream)));
     count_launch();
     return DEVIAS_OK;
   }
@@ -474,10 +539,9 @@ extern "C" int devias_skinny_outer(const float* a, const int64_t* a_map, const f
   if (M > skinny_max_rows()) {
     TileArgs t{};
     t.A = a; t.B = b; t.C = c; t.am = make_map(a_map); t.bm = make_map(b_map); t.c_batch = c_batch;
-    t.I = I; t.J = J; t.L = M; t.ldc = J; t.l_per_split = (M + kTgK - 1) / kTgK * kTgK; t.accumulate = accumulate;
+    t.I = I; t.J = J; t.L = M; t.ldc = J; t.accumulate = accumulate;
     t.colsum = colsum; t.colsum_batch = colsum_batch;
-    DV_CHECK_CUDA(launch_k(tile_gemm_kernel<2>, dim3((J + kTg - 1) / kTg, (I + kTg - 1) / kTg, batch), dim3(256), (size_t)0,
-                           (cudaStream_t)stream, t, 1));
+    DV_CHECK_CUDA((launch_tile<2, 1>(t, batch, false, (cudaStream_t)stream)));   // each output belongs to one CTA: no split
     count_launch();
     return DEVIAS_OK;
   }

@@ -17,7 +17,8 @@ def timeit(fn, n=50):
     return e0.elapsed_time(e1) * 1e3 / n
 
 
-for M, K, N in [(16, 768, 3072), (16, 3072, 768), (16, 768, 2048), (16, 2048, 768), (16, 768, 466), (64, 768, 3072)]:
+for M, K, N in [(16, 768, 3072), (16, 3072, 768), (16, 768, 2048), (16, 2048, 768), (16, 768, 466), (64, 768, 3072), (64, 3072, 768),
+                (64, 768, 2048), (64, 2048, 768), (64, 768, 765), (512, 768, 3072)]:
     x = torch.randn(M, K, device='cuda', requires_grad=True); w = (torch.randn(N, K, device='cuda') * 0.05).requires_grad_(True)
     b = torch.zeros(N, device='cuda', requires_grad=True); dy = torch.randn(M, N, device='cuda')
     row = []
