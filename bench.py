@@ -266,7 +266,10 @@ def measure_train(name, cfg, args, dev, world, rank, with_roofline=True, with_e2
     cuts = [int(c) for c in args.cuts.split(',') if c.strip().isdigit()]
     # ---------------------------------------------------------------- warm-up (+ graph capture of the whole step)
     use_graph = not args.no_graph
-    for i in range(max(args.warmup, 3) if not use_graph else 1):
+    # (DEVIAS_BENCH_LAUNCH_LIST=1: the ncu launch-list run of tools/evidence.sh -- eager, --warmup steps exactly, no roofline leg;
+    #  every extra step costs minutes under the profiler.  Its printed numbers are not bench values.)
+    launch_list = bool(os.environ.get('DEVIAS_BENCH_LAUNCH_LIST')) and not use_graph
+    for i in range((args.warmup if launch_list else max(args.warmup, 3)) if not use_graph else 1):
         step(devb[i % nbuf])
     barrier()
     graphed = None
@@ -356,7 +359,7 @@ def measure_train(name, cfg, args, dev, world, rank, with_roofline=True, with_e2
                 acc[k][0] += t; acc[k][1] += w; acc[k][2] += n
         pstep.close()
         prof = {'reps': reps, 'ms_per_step_instrumented': tot / reps, 'kinds': acc}
-    elif with_roofline:
+    elif with_roofline and not launch_list:
         _lib.profile_begin()
         pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         pe0.record()
@@ -379,23 +382,36 @@ def slot_grid(dev, peak_gbs):
     import torch
     from devias_b200 import ops
 
-    def timeit(fn, n):
+    def timeit(fn, n, graph_calls=0):
         """ms per call; warm-up and timed region are both >= ~40 ms long so that the SM clock has settled on this (memory-bound)
-        load after the power-capped GEMM phases that ran before"""
+        load after the power-capped GEMM phases that ran before.  graph_calls > 0: that many calls are captured into one CUDA
+        graph and the graph is replayed -- below ~64 clips a call is shorter than the ~30 us the python / ctypes launch path
+        takes, and the aggregation block's callers replay it from a graph anyway"""
+        if graph_calls:
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for _ in range(graph_calls):
+                    fn()
+            call, per_call = g.replay, graph_calls
+        else:
+            call, per_call = fn, 1
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize(); s0.record()
         for _ in range(3):
-            fn()
+            call()
         s1.record(); torch.cuda.synchronize()
         per = max(s0.elapsed_time(s1) / 3, 1e-3)
-        reps = int(min(max(n, 40.0 / per), 2000))
+        reps = int(min(max(n / per_call, 40.0 / per), 2000))
         for _ in range(reps):
-            fn()
+            call()
         torch.cuda.synchronize(); s0.record()
         for _ in range(reps):
-            fn()
+            call()
         s1.record(); torch.cuda.synchronize()
-        return s0.elapsed_time(s1) / reps
+        return s0.elapsed_time(s1) / reps / per_call
 
     out = []
     for dt in (torch.float32, torch.bfloat16):
@@ -418,20 +434,21 @@ def slot_grid(dev, peak_gbs):
                         cnt[0] += 1
                         return ops.slot_stream_fwd(toks[cnt[0] % copies], g_, G_, c0_)
                     n = 10 if Bm >= 64 else 2 * copies if copies > 10 else 20
-                    tf = timeit(fwd, n)
+                    gc = 0 if Bm >= 64 else 2 * copies            # small batches: graph replay (every rotating copy twice per replay)
+                    tf = timeit(fwd, n, gc)
                     U_, m_, A_, at_, mu_, r_ = ops.slot_stream_fwd(tok, g_, G_, c0_)
                     dU_, dm_, dA_ = torch.randn_like(U_), torch.randn_like(m_), torch.randn_like(A_)
 
                     def bwd():
                         cnt[0] += 1
                         return ops.slot_stream_bwd(toks[cnt[0] % copies], mu_, r_, g_, G_, at_, dU_, dm_, dA_)
-                    tb = timeit(bwd, n)
+                    tb = timeit(bwd, n, gc)
                     fb = nbytes + Bm * 4 * S * 1568 * 4            # tokens once + the returned slot-axis softmax
                     bb = nbytes + Bm * 1568 * 768 * 4              # tokens once + the token gradient written once
                     out.append({'S': S, 'batch': Bm, 'tokens': 'f32' if dt is torch.float32 else 'bf16',
                                 'fwd_us': tf * 1e3, 'fwd_gbs': fb / tf / 1e6, 'fwd_frac': fb / tf / 1e6 / peak_gbs,
                                 'bwd_us': tb * 1e3, 'bwd_gbs': bb / tb / 1e6, 'bwd_frac': bb / tb / 1e6 / peak_gbs,
-                                'rotating_copies': copies})
+                                'rotating_copies': copies, 'launch': 'cuda-graph replay' if gc else 'eager'})
                     del tok, toks, g_, G_, c0_, U_, m_, A_, at_, mu_, r_, dU_, dm_, dA_
                 except Exception as e:  # the grid must never take the headline down
                     out.append({'S': S, 'batch': Bm, 'error': repr(e)[:200]})

@@ -9,6 +9,8 @@ p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'M
 if os.path.isfile(p):
     PEAK = json.load(open(p)).get('hbm_gbs', PEAK)
 def t(fn, n=20):
+    if os.environ.get('DEVIAS_ONESHOT'):       # one launch per case for `ncu -c <cases>`
+        fn(); torch.cuda.synchronize(); return 1.0
     for _ in range(3): fn()
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
